@@ -1,0 +1,604 @@
+// force2vec_b200/csrc/f2v_engine.cu -- the C ABI of include/f2v.h: device state, the
+// per-minibatch work plan, kernel dispatch.  Host-side only bookkeeping; all arithmetic
+// of the force step is in f2v_kernels.cuh.  There is no CPU fallback in this file.
+#include "../../include/f2v.h"
+#include "f2v_kernels.cuh"
+#include "f2v_plan.hpp"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace f2v;
+
+// ------------------------------------------------------------------ errors -------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(F2V_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+// ------------------------------------------------------------------ NCCL (dlopen) ------
+// NCCL is loaded lazily so that the single-GPU path has no link-time dependency on it.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.handle) return F2V_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(F2V_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather)
+        return fail(F2V_ERR_NCCL, "libnccl is missing required symbols");
+    g_nccl.handle = h;
+    return F2V_OK;
+}
+#define NC(call)                                                                                 \
+    do {                                                                                         \
+        int _r = (call);                                                                         \
+        if (_r != 0)                                                                             \
+            return fail(F2V_ERR_NCCL, "%s failed: %s", #call,                                    \
+                        g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error");       \
+    } while (0)
+constexpr int kNcclFloat32 = 7;   // ncclFloat32 in nccl.h's ncclDataType_t
+
+// ------------------------------------------------------------------ engine -------------
+struct Plan {
+    uint32_t batch = 0, chunk = 0;
+    bool walk = false;
+    int rank = 0, world = 1;
+    uint64_t first_row = 0, nrows = 0;      // row range covered (whole table for epochs)
+    uint64_t nb = 0;
+    std::vector<uint64_t> item_ptr;         // nb+1 offsets into items / hub
+    std::vector<uint32_t> n_hub;            // hub-chunk items at the front of each minibatch
+    Item* d_items = nullptr;
+    HubInfo* d_hub = nullptr;
+    uint64_t cap_items = 0;
+    uint32_t max_slots = 0;
+};
+
+struct f2v_engine {
+    int device = 0;
+    uint64_t n = 0, nnz = 0;
+    uint32_t dim = 0;
+    std::vector<uint64_t> h_rowptr;          // host copy: the plan is built from degrees
+    uint64_t* d_rowptr = nullptr;
+    uint32_t* d_colids = nullptr;
+    float* d_X[2] = {nullptr, nullptr};      // ping-pong tables; cur holds the live embedding
+    int cur = 0;
+    uint64_t rows_alloc = 0;                 // rows allocated per table (n padded for all-gather)
+    float* d_lut = nullptr;
+    bool lut_set = false;
+    uint32_t* d_neg = nullptr;
+    uint64_t neg_cap = 0, neg_count = 0, neg_off = 0;
+    uint32_t* d_walks = nullptr;
+    bool walks_set = false;
+    float* d_stage = nullptr;
+    uint64_t stage_cap = 0;
+    float* d_partials = nullptr;
+    uint32_t* d_counters = nullptr;
+    uint64_t slots_cap = 0;
+    Plan epoch_plan, step_plan;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    int epoch_mode = 0;
+    uint64_t launches = 0;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int sm_count = 0;
+};
+
+static int ensure(void** p, uint64_t* cap, uint64_t need_bytes) {
+    if (*cap >= need_bytes && *p) return F2V_OK;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(p, need_bytes ? need_bytes : 16));
+    *cap = need_bytes;
+    return F2V_OK;
+}
+
+// Upload the host plan (f2v_plan.hpp) for rows [first_row, first_row+nrows) and size the
+// hub-row partial buffers.  Cached on (batch, chunk, walk, rank, world, range).
+static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrows, uint32_t batch,
+                      uint32_t chunk, bool walk, int rank, int world) {
+    if (pl.d_items && pl.batch == batch && pl.chunk == chunk && pl.walk == walk && pl.rank == rank &&
+        pl.world == world && pl.first_row == first_row && pl.nrows == nrows)
+        return F2V_OK;
+    HostPlan hp;
+    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, walk, rank, world, hp);
+    const uint64_t nb = hp.nb, total = hp.items.size();
+    std::vector<Item>& items = hp.items;
+    std::vector<HubInfo>& hub = hp.hub;
+    std::vector<uint64_t>& item_ptr = hp.item_ptr;
+    std::vector<uint32_t>& n_hub = hp.n_hub;
+    const uint32_t max_slots = hp.max_slots;
+    if (pl.cap_items < total || !pl.d_items) {
+        if (pl.d_items) CU(cudaFree(pl.d_items));
+        if (pl.d_hub) CU(cudaFree(pl.d_hub));
+        pl.d_items = nullptr; pl.d_hub = nullptr; pl.cap_items = 0;
+        CU(cudaMalloc((void**)&pl.d_items, sizeof(Item) * (total ? total : 1)));
+        CU(cudaMalloc((void**)&pl.d_hub, sizeof(HubInfo) * (total ? total : 1)));
+        pl.cap_items = total;
+    }
+    // plans are (re)built rarely; a synchronous copy keeps the host vectors' lifetime simple
+    CU(cudaStreamSynchronize(e->stream));
+    if (total) {
+        CU(cudaMemcpy(pl.d_items, items.data(), sizeof(Item) * total, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(pl.d_hub, hub.data(), sizeof(HubInfo) * total, cudaMemcpyHostToDevice));
+    }
+    if (max_slots > e->slots_cap || !e->d_partials) {
+        if (e->d_partials) CU(cudaFree(e->d_partials));
+        if (e->d_counters) CU(cudaFree(e->d_counters));
+        e->d_partials = nullptr; e->d_counters = nullptr;
+        uint64_t slots = std::max<uint64_t>(max_slots, 1);
+        CU(cudaMalloc((void**)&e->d_partials, sizeof(float) * slots * e->dim));
+        CU(cudaMalloc((void**)&e->d_counters, sizeof(uint32_t) * slots));
+        CU(cudaMemset(e->d_counters, 0, sizeof(uint32_t) * slots));
+        e->slots_cap = slots;
+    }
+    pl.batch = batch; pl.chunk = chunk; pl.walk = walk; pl.rank = rank; pl.world = world;
+    pl.first_row = first_row; pl.nrows = nrows; pl.nb = nb;
+    pl.item_ptr.swap(item_ptr);
+    pl.n_hub.swap(n_hub);
+    pl.max_slots = max_slots;
+    return F2V_OK;
+}
+
+// ------------------------------------------------------------------ dispatch -----------
+template <class L, int MODEL>
+static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st) {
+    if (p.n_items == 0) return cudaSuccess;
+    size_t smem = 0;
+    if (L::kBulk && p.neg_in_smem) smem = 128 + (size_t)p.s * p.dim * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(force_batch_kernel<L, MODEL>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    unsigned grid = (p.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
+    force_batch_kernel<L, MODEL><<<grid, kWarpsPerCta * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <class L>
+static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t st) {
+    switch (model) {
+    case kTDist: return launch_batch_t<L, kTDist>(p, st);
+    case kSigmoid: return launch_batch_t<L, kSigmoid>(p, st);
+    default: return launch_batch_t<L, kWalk>(p, st);
+    }
+}
+
+static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st) {
+    switch (p.dim) {
+    case 32: return launch_batch_m<VecL<32>>(model, p, st);
+    case 64: return launch_batch_m<VecL<64>>(model, p, st);
+    case 128: return launch_batch_m<VecL<128>>(model, p, st);
+    case 256: return launch_batch_m<VecL<256>>(model, p, st);
+    default: break;
+    }
+    if (p.dim <= 32) return launch_batch_m<GenL<1>>(model, p, st);
+    if (p.dim <= 64) return launch_batch_m<GenL<2>>(model, p, st);
+    if (p.dim <= 128) return launch_batch_m<GenL<4>>(model, p, st);
+    if (p.dim <= 256) return launch_batch_m<GenL<8>>(model, p, st);
+    if (p.dim <= 512) return launch_batch_m<GenL<16>>(model, p, st);
+    return launch_batch_m<GenL<32>>(model, p, st);
+}
+
+static bool bulk_ok(const f2v_engine* e, uint32_t s, int bs_mode) {
+    if (bs_mode != 0 || s == 0) return false;
+    if (!(e->dim == 32 || e->dim == 64 || e->dim == 128 || e->dim == 256)) return false;
+    return 128 + (size_t)s * e->dim * sizeof(float) <= 200 * 1024;
+}
+
+static int check_model(const f2v_engine* e, int model, uint32_t s, int bs_mode) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    if (model != F2V_TDIST && model != F2V_SIGMOID && model != F2V_WALK)
+        return fail(F2V_ERR_ARG, "model must be 5, 6 or 7 (got %d)", model);
+    if (bs_mode != 0 && bs_mode != 1) return fail(F2V_ERR_ARG, "bs_mode must be 0 or 1");
+    if (model != F2V_TDIST && !e->lut_set) return fail(F2V_ERR_STATE, "sigmoid table not set (f2v_set_lut)");
+    if (model == F2V_WALK && !e->walks_set) return fail(F2V_ERR_STATE, "walks not set (f2v_set_walks / f2v_sample_walks)");
+    (void)s;
+    return F2V_OK;
+}
+
+static uint64_t neg_stride(int model, uint32_t batch, uint32_t s, int bs_mode) {
+    return (bs_mode && model != F2V_WALK) ? (uint64_t)batch + s - 1 : (uint64_t)s;
+}
+
+// ------------------------------------------------------------------ C ABI --------------
+extern "C" {
+
+const char* f2v_last_error(void) { return g_err; }
+int f2v_abi_version(void) { return F2V_ABI_VERSION; }
+
+int f2v_device_count(void) {
+    int c = 0;
+    cudaError_t r = cudaGetDeviceCount(&c);
+    if (r != cudaSuccess) return fail(F2V_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(r));
+    return c;
+}
+
+int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz, const uint64_t* rowptr,
+               const uint32_t* colids, uint32_t dim) {
+    if (!out) return fail(F2V_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n < 2 || n > 0xffffffffull) return fail(F2V_ERR_ARG, "n must be in [2, 2^32)");
+    if (dim < 1 || dim > 1024) return fail(F2V_ERR_ARG, "dim must be in [1, 1024]");
+    if (!rowptr || (nnz > 0 && !colids)) return fail(F2V_ERR_ARG, "null CSR arrays");
+    if (rowptr[0] != 0 || rowptr[n] != nnz) return fail(F2V_ERR_ARG, "rowptr[0] must be 0 and rowptr[n] == nnz");
+    for (uint64_t i = 0; i < n; i++)
+        if (rowptr[i + 1] < rowptr[i]) return fail(F2V_ERR_ARG, "rowptr not monotone at row %llu", (unsigned long long)i);
+    for (uint64_t k = 0; k < nnz; k++)
+        if (colids[k] >= n) return fail(F2V_ERR_ARG, "colids[%llu] = %u out of range", (unsigned long long)k, colids[k]);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device_id < 0 || device_id >= ndev) return fail(F2V_ERR_ARG, "device %d not in [0,%d)", device_id, ndev);
+    CU(cudaSetDevice(device_id));
+    f2v_engine* e = new (std::nothrow) f2v_engine();
+    if (!e) return fail(F2V_ERR_NOMEM, "out of host memory");
+    e->device = device_id; e->n = n; e->nnz = nnz; e->dim = dim;
+    e->h_rowptr.assign(rowptr, rowptr + n + 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_id));
+    e->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) { delete e; return fail(F2V_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); }
+    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    CU(cudaEventCreate(&e->ev0));
+    CU(cudaEventCreate(&e->ev1));
+    CU(cudaMalloc((void**)&e->d_rowptr, sizeof(uint64_t) * (n + 1)));
+    CU(cudaMalloc((void**)&e->d_colids, sizeof(uint32_t) * (nnz ? nnz : 1)));
+    CU(cudaMemcpy(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice));
+    if (nnz) CU(cudaMemcpy(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
+    e->rows_alloc = n;
+    CU(cudaMalloc((void**)&e->d_X[0], sizeof(float) * n * dim));
+    CU(cudaMemset(e->d_X[0], 0, sizeof(float) * n * dim));
+    CU(cudaMalloc((void**)&e->d_lut, sizeof(float) * kLutAlloc));
+    *out = e;
+    return F2V_OK;
+}
+
+int f2v_destroy(f2v_engine* e) {
+    if (!e) return F2V_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_X[0]); cudaFree(e->d_X[1]);
+    cudaFree(e->d_lut); cudaFree(e->d_neg); cudaFree(e->d_walks); cudaFree(e->d_stage);
+    cudaFree(e->d_partials); cudaFree(e->d_counters);
+    cudaFree(e->epoch_plan.d_items); cudaFree(e->epoch_plan.d_hub);
+    cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return F2V_OK;
+}
+
+int f2v_host_alloc(void** p, uint64_t bytes) {
+    if (!p) return fail(F2V_ERR_ARG, "null argument");
+    *p = nullptr;
+    CU(cudaMallocHost(p, bytes ? bytes : 16));
+    return F2V_OK;
+}
+
+int f2v_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return F2V_OK;
+}
+
+int f2v_set_stream(f2v_engine* e, void* cuda_stream) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return F2V_OK;
+}
+
+int f2v_sync(f2v_engine* e) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_set_embeddings(f2v_engine* e, const float* X) {
+    if (!e || !X) return fail(F2V_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->d_X[e->cur], X, sizeof(float) * e->n * e->dim, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_get_embeddings(f2v_engine* e, float* X) {
+    if (!e || !X) return fail(F2V_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(X, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_get_rows(f2v_engine* e, uint64_t first_row, uint64_t nrows, float* rows) {
+    if (!e || !rows) return fail(F2V_ERR_ARG, "null argument");
+    if (first_row + nrows > e->n) return fail(F2V_ERR_ARG, "row range out of bounds");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(rows, e->d_X[e->cur] + first_row * e->dim, sizeof(float) * nrows * e->dim,
+                       cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_set_lut(f2v_engine* e, const float* t, uint32_t count) {
+    if (!e || !t) return fail(F2V_ERR_ARG, "null argument");
+    if (count != kLutSize && count != kLutSize + 1) return fail(F2V_ERR_ARG, "sigmoid table must have 2048 entries");
+    float h[kLutAlloc];
+    memcpy(h, t, sizeof(float) * kLutSize);
+    for (int i = kLutSize; i < kLutAlloc; i++) h[i] = 1.0f;   // v == 6.0f exactly: defined as 1.0
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->d_lut, h, sizeof(h), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->lut_set = true;
+    return F2V_OK;
+}
+
+int f2v_set_negatives(f2v_engine* e, const uint32_t* idx, uint64_t count) {
+    if (!e || (!idx && count)) return fail(F2V_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    if (e->neg_cap < count || !e->d_neg) {
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->d_neg) CU(cudaFree(e->d_neg));
+        e->d_neg = nullptr;
+        e->neg_cap = 0;
+        CU(cudaMalloc((void**)&e->d_neg, sizeof(uint32_t) * (count ? count : 1)));
+        e->neg_cap = count;
+    }
+    if (count) CU(cudaMemcpyAsync(e->d_neg, idx, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, e->stream));
+    e->neg_count = count;
+    e->neg_off = 0;
+    return F2V_OK;
+}
+
+int f2v_set_negative_offset(f2v_engine* e, uint64_t offset) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    if (offset > e->neg_count) return fail(F2V_ERR_ARG, "offset beyond the resident stream");
+    e->neg_off = offset;
+    return F2V_OK;
+}
+
+static int ensure_walks(f2v_engine* e) {
+    if (!e->d_walks) CU(cudaMalloc((void**)&e->d_walks, sizeof(uint32_t) * e->n * kWalkLen));
+    return F2V_OK;
+}
+
+int f2v_set_walks(f2v_engine* e, const uint32_t* walks) {
+    if (!e || !walks) return fail(F2V_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    int r = ensure_walks(e);
+    if (r) return r;
+    CU(cudaMemcpyAsync(e->d_walks, walks, sizeof(uint32_t) * e->n * kWalkLen, cudaMemcpyHostToDevice, e->stream));
+    e->walks_set = true;
+    return F2V_OK;
+}
+
+int f2v_get_walks(f2v_engine* e, uint32_t* walks) {
+    if (!e || !walks) return fail(F2V_ERR_ARG, "null argument");
+    if (!e->walks_set) return fail(F2V_ERR_STATE, "no walks resident");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(walks, e->d_walks, sizeof(uint32_t) * e->n * kWalkLen, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_sample_walks(f2v_engine* e, uint64_t seed, uint64_t epoch) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    int r = ensure_walks(e);
+    if (r) return r;
+    unsigned grid = (unsigned)((e->n + 255) / 256);
+    walk_kernel<<<grid, 256, 0, e->stream>>>(e->n, e->nnz, e->d_rowptr, e->d_colids, e->d_walks, seed, epoch);
+    CU(cudaGetLastError());
+    e->launches++;
+    e->walks_set = true;
+    return F2V_OK;
+}
+
+int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const uint32_t* neg_idx,
+             uint32_t s, int bs_mode, float lr, const uint32_t* walks) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    if (model == F2V_WALK) bs_mode = 0;     // -bs is ignored by option 7 (Test/Force2Vec.cpp:148-150)
+    CU(cudaSetDevice(e->device));
+    if (model == F2V_WALK && walks) { int r = f2v_set_walks(e, walks); if (r) return r; }
+    int r = check_model(e, model, s, bs_mode);
+    if (r) return r;
+    if (nrows == 0) return F2V_OK;
+    if (first_row + nrows > e->n) return fail(F2V_ERR_ARG, "row range out of bounds");
+    if (s > 0 && !neg_idx) return fail(F2V_ERR_ARG, "neg_idx is null");
+    r = f2v_set_negatives(e, neg_idx, neg_stride(model, nrows, s, bs_mode));
+    if (r) return r;
+    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 64, model == F2V_WALK, 0, 1);
+    if (r) return r;
+    uint64_t cap_bytes = e->stage_cap;
+    r = ensure((void**)&e->d_stage, &cap_bytes, sizeof(float) * (uint64_t)nrows * e->dim);
+    if (r) return r;
+    e->stage_cap = cap_bytes;
+    BatchParams p{};
+    p.items = e->step_plan.d_items; p.hub = e->step_plan.d_hub;
+    p.n_items = (uint32_t)e->step_plan.item_ptr[1]; p.n_hub = e->step_plan.n_hub[0];
+    p.lo = first_row; p.split = 0;
+    p.Xlo = e->d_X[e->cur]; p.Xhi = e->d_X[e->cur];
+    p.out = e->d_stage; p.out_base = first_row;
+    p.colids = e->d_colids; p.neg = e->d_neg; p.walks = e->d_walks; p.lut = e->d_lut;
+    p.partials = e->d_partials; p.counters = e->d_counters;
+    p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
+    p.lr = lr;
+    CU(launch_batch(model, p, e->stream));
+    e->launches++;
+    // apply after the join (algorithms.cpp:629-639 / :913-921)
+    CU(cudaMemcpyAsync(e->d_X[e->cur] + first_row * e->dim, e->d_stage, sizeof(float) * (uint64_t)nrows * e->dim,
+                       cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode, float lr, uint32_t chunk) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    if (model == F2V_WALK) bs_mode = 0;
+    int r = check_model(e, model, s, bs_mode);
+    if (r) return r;
+    if (batch == 0) return fail(F2V_ERR_ARG, "batch must be > 0");
+    if (e->world > 1 && batch % e->world) return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
+    CU(cudaSetDevice(e->device));
+    if (chunk == 0) chunk = 64;
+    const uint64_t nb = (e->n + batch - 1) / batch;
+    const uint64_t W = neg_stride(model, batch, s, bs_mode);
+    if (e->neg_count < e->neg_off + nb * W)
+        return fail(F2V_ERR_STATE, "negative stream too short: have %llu (offset %llu), epoch needs %llu",
+                    (unsigned long long)e->neg_count, (unsigned long long)e->neg_off, (unsigned long long)(nb * W));
+    // tables: the all-gather works on whole minibatches, so pad the row count to nb*batch
+    const uint64_t rows_needed = e->world > 1 ? nb * batch : e->n;
+    if (e->rows_alloc < rows_needed) {
+        CU(cudaStreamSynchronize(e->stream));
+        float* nx = nullptr;
+        CU(cudaMalloc((void**)&nx, sizeof(float) * rows_needed * e->dim));
+        CU(cudaMemset(nx, 0, sizeof(float) * rows_needed * e->dim));
+        CU(cudaMemcpy(nx, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToDevice));
+        CU(cudaFree(e->d_X[e->cur]));
+        e->d_X[e->cur] = nx;
+        if (e->d_X[1 - e->cur]) { CU(cudaFree(e->d_X[1 - e->cur])); e->d_X[1 - e->cur] = nullptr; }
+        e->rows_alloc = rows_needed;
+    }
+    if (!e->d_X[1 - e->cur]) {
+        CU(cudaMalloc((void**)&e->d_X[1 - e->cur], sizeof(float) * e->rows_alloc * e->dim));
+        CU(cudaMemsetAsync(e->d_X[1 - e->cur], 0, sizeof(float) * e->rows_alloc * e->dim, e->stream));
+    }
+    r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, model == F2V_WALK, e->rank, e->world);
+    if (r) return r;
+    const Plan& pl = e->epoch_plan;
+    float* Xold = e->d_X[e->cur];
+    float* Xnew = e->d_X[1 - e->cur];
+    CU(cudaEventRecord(e->ev0, e->stream));
+    BatchParams p{};
+    p.Xlo = Xnew; p.Xhi = Xold; p.out = Xnew; p.out_base = 0;
+    p.colids = e->d_colids; p.walks = e->d_walks; p.lut = e->d_lut;
+    p.partials = e->d_partials; p.counters = e->d_counters;
+    p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
+    p.lr = lr;
+    const uint64_t slice = batch / (uint64_t)e->world;
+    for (uint64_t b = 0; b < nb; b++) {
+        p.items = pl.d_items + pl.item_ptr[b];
+        p.hub = pl.d_hub + pl.item_ptr[b];
+        p.n_items = (uint32_t)(pl.item_ptr[b + 1] - pl.item_ptr[b]);
+        p.n_hub = pl.n_hub[b];
+        p.lo = b * batch;
+        p.split = b * batch;
+        p.neg = e->d_neg + e->neg_off + b * W;
+        if (p.n_items) {
+            CU(launch_batch(model, p, e->stream));
+            e->launches++;
+        }
+        if (e->world > 1) {
+            // exchange the updated slices before the next minibatch reads them
+            float* base = Xnew + b * batch * e->dim;
+            NC(g_nccl.AllGather(base + (uint64_t)e->rank * slice * e->dim, base, slice * e->dim,
+                                kNcclFloat32, e->comm, e->stream));
+        }
+    }
+    CU(cudaEventRecord(e->ev1, e->stream));
+    e->ev_valid = true;
+    e->cur = 1 - e->cur;
+    return F2V_OK;
+}
+
+int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode, float lr,
+                       uint32_t chunk, const float* X_in, const uint32_t* neg, uint64_t neg_count,
+                       const uint32_t* walks, float* X_out) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    int r;
+    if (X_in)
+        CU(cudaMemcpyAsync(e->d_X[e->cur], X_in, sizeof(float) * e->n * e->dim, cudaMemcpyHostToDevice, e->stream));
+    if (neg) { r = f2v_set_negatives(e, neg, neg_count); if (r) return r; }
+    if (walks) { r = f2v_set_walks(e, walks); if (r) return r; }
+    r = f2v_run_epoch(e, model, batch, s, bs_mode, lr, chunk);
+    if (r) return r;
+    if (X_out)
+        CU(cudaMemcpyAsync(X_out, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return F2V_OK;
+}
+
+int f2v_set_epoch_mode(f2v_engine* e, int mode) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    if (mode != 0) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
+    e->epoch_mode = mode;
+    return F2V_OK;
+}
+
+uint64_t f2v_launch_count(const f2v_engine* e) { return e ? e->launches : 0; }
+
+int f2v_last_epoch_ms(f2v_engine* e, float* ms) {
+    if (!e || !ms) return fail(F2V_ERR_ARG, "null argument");
+    if (!e->ev_valid) return fail(F2V_ERR_STATE, "no epoch has run");
+    CU(cudaSetDevice(e->device));
+    CU(cudaEventSynchronize(e->ev1));
+    CU(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return F2V_OK;
+}
+
+int f2v_comm_unique_id(void* id128) {
+    if (!id128) return fail(F2V_ERR_ARG, "null argument");
+    int r = nccl_load();
+    if (r) return r;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return F2V_OK;
+}
+
+int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world) {
+    if (!e || !id128) return fail(F2V_ERR_ARG, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(F2V_ERR_ARG, "bad rank/world");
+    if (e->comm) return fail(F2V_ERR_STATE, "communicator already initialised");
+    int r = nccl_load();
+    if (r) return r;
+    CU(cudaSetDevice(e->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NC(g_nccl.CommInitRank(&e->comm, world, id, rank));
+    e->rank = rank;
+    e->world = world;
+    return F2V_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,542 @@
+// force2vec_b200/csrc/f2v_host.cpp -- host side of the drop-in (include/f2v_host.h):
+// glibc-compatible rand() stream and the samplers that consume it, MatrixMarket loader,
+// .embd writer, R-MAT generator, and the whole-run driver that replaces the bodies of
+// algorithms::AlgoForce2Vec*() with calls into the GPU engine (include/f2v.h).
+#include "../../include/f2v_host.h"
+#include "../../include/f2v.h"
+#include "f2v_host.hpp"
+#include "f2v_plan.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+// ------------------------------------------------------------------ rand() stream ------
+// glibc random_r.c TYPE_3: degree 31, separation 3.  srandom: r[0] = seed, r[i] =
+// 16807*r[i-1] mod (2^31-1) (Schrage), then 310 outputs are discarded; random: r[f] += r[b],
+// output r[f] >> 1.  Call sites replaced: Test/Force2Vec.cpp:126, algorithms.cpp:42,50,56.
+struct f2v_rng {
+    uint32_t r[31];
+    int f, b;
+    inline uint32_t next() {
+        uint32_t v = r[f] + r[b];
+        r[f] = v;
+        if (++f == 31) f = 0;
+        if (++b == 31) b = 0;
+        return v >> 1;
+    }
+};
+
+extern "C" f2v_rng* f2v_rng_create(uint32_t seed) {
+    f2v_rng* g = (f2v_rng*)malloc(sizeof(f2v_rng));
+    if (!g) return nullptr;
+    if (seed == 0) seed = 1;
+    int32_t w = (int32_t)seed;
+    g->r[0] = (uint32_t)w;
+    for (int i = 1; i < 31; i++) {
+        long hi = w / 127773, lo = w % 127773;
+        long t = 16807 * lo - 2836 * hi;
+        if (t < 0) t += 2147483647;
+        w = (int32_t)t;
+        g->r[i] = (uint32_t)w;
+    }
+    g->f = 3;
+    g->b = 0;
+    for (int i = 0; i < 310; i++) g->next();
+    return g;
+}
+extern "C" void f2v_rng_destroy(f2v_rng* g) { free(g); }
+extern "C" int32_t f2v_rng_next(f2v_rng* g) { return (int32_t)g->next(); }
+
+extern "C" int f2v_init_embeddings(f2v_rng* g, int model, uint64_t n, uint32_t dim, float* X) {
+    if (!g || !X) return F2V_ERR_ARG;
+    const double denom = 2147483647.0 + 1.0;   // RAND_MAX + 1.0
+    const uint64_t total = n * (uint64_t)dim;
+    if (model == F2V_TDIST)
+        for (uint64_t k = 0; k < total; k++) X[k] = (float)(-1.0 + 2.0 * (double)g->next() / denom);
+    else
+        for (uint64_t k = 0; k < total; k++) X[k] = (float)((double)g->next() / denom);
+    return F2V_OK;
+}
+
+extern "C" int f2v_build_lut(float* t) {
+    if (!t) return F2V_ERR_ARG;
+    for (int i = 0; i < F2V_LUT_SIZE; i++) {
+        // VALUETYPE x = 2.0*SM_BOUND*i/SM_TABLE_SIZE - SM_BOUND; 1.0/(1+exp(-x)) with the float exp
+        float x = (float)(2.0 * 6.0 * i / F2V_LUT_SIZE - 6.0);
+        float e = 1 + std::exp(-x);
+        t[i] = (float)(1.0 / e);
+    }
+    return F2V_OK;
+}
+
+extern "C" uint64_t f2v_neg_stream_len(int model, uint64_t n, uint32_t batch, uint32_t s, int bs_mode) {
+    if (batch == 0) return 0;
+    const uint64_t nb = (n + batch - 1) / batch;
+    const uint64_t W = (bs_mode && model != F2V_WALK) ? (uint64_t)batch + s - 1 : (uint64_t)s;
+    return nb * W;
+}
+
+extern "C" int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint32_t batch, uint32_t s,
+                                        int bs_mode, uint32_t* out) {
+    if (!g || !out || batch == 0 || n < 2) return F2V_ERR_ARG;
+    const uint64_t nb = (n + batch - 1) / batch;
+    const bool window = bs_mode && model != F2V_WALK;
+    const uint64_t W = window ? (uint64_t)batch + s - 1 : (uint64_t)s;
+    const uint64_t draws = window ? (uint64_t)s * batch : (uint64_t)s;
+    for (uint64_t b = 0; b < nb; b++) {
+        uint32_t maxv = (uint32_t)(n - 1);
+        if (model == F2V_WALK) {
+            uint64_t pre = (b + 1) * (uint64_t)batch;
+            if (pre < maxv) maxv = (uint32_t)pre;
+        }
+        uint32_t* o = out + b * W;
+        for (uint64_t k = 0; k < draws; k++) {
+            uint32_t r = g->next() % maxv;
+            if (k < W) o[k] = r;      // s*batch draws are consumed, batch+s-1 are ever read
+        }
+    }
+    return F2V_OK;
+}
+
+extern "C" int f2v_draw_walks(f2v_rng* g, uint64_t n, uint64_t nnz, const uint64_t* rowptr,
+                              const uint32_t* colids, uint32_t* walks) {
+    if (!g || !rowptr || !walks) return F2V_ERR_ARG;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t w = i;
+        for (int l = 0; l < F2V_WALKLEN; l++) {
+            const uint64_t dg = rowptr[w + 1] - rowptr[w];
+            uint64_t e = w;   // the reference indexes colids[] with the vertex id here
+            if (dg > 2) e = rowptr[w] + g->next() % (uint32_t)(dg - 1);
+            else if (dg == 2) e = rowptr[w];
+            const uint32_t nx = e < nnz ? colids[e] : (uint32_t)w;
+            walks[i * F2V_WALKLEN + l] = nx;
+            w = nx;
+        }
+    }
+    return F2V_OK;
+}
+
+// ------------------------------------------------------------------ graph IO -----------
+static int csr_from_pairs(uint64_t n, std::vector<uint32_t>& src, std::vector<uint32_t>& dst, bool dedupe,
+                          uint64_t* nnz_out, uint64_t** rowptr_out, uint32_t** colids_out) {
+    const uint64_t m = src.size();
+    uint64_t* rowptr = (uint64_t*)calloc(n + 1, sizeof(uint64_t));
+    if (!rowptr) return F2V_ERR_NOMEM;
+    for (uint64_t k = 0; k < m; k++) rowptr[src[k] + 1]++;
+    for (uint64_t i = 0; i < n; i++) rowptr[i + 1] += rowptr[i];
+    uint32_t* colids = (uint32_t*)malloc(sizeof(uint32_t) * (m ? m : 1));
+    if (!colids) { free(rowptr); return F2V_ERR_NOMEM; }
+    {
+        std::vector<uint64_t> cur(rowptr, rowptr + n);
+        for (uint64_t k = 0; k < m; k++) colids[cur[src[k]]++] = dst[k];
+    }
+    std::vector<uint32_t>().swap(src);
+    std::vector<uint32_t>().swap(dst);
+    std::vector<uint64_t> newdeg(dedupe ? n : 0);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        uint32_t* b = colids + rowptr[i];
+        uint32_t* e = colids + rowptr[i + 1];
+        std::sort(b, e);
+        if (dedupe) newdeg[i] = (uint64_t)(std::unique(b, e) - b);
+    }
+    if (dedupe) {
+        uint64_t w = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            const uint64_t r0 = rowptr[i];
+            rowptr[i] = w;
+            if (w != r0) memmove(colids + w, colids + r0, sizeof(uint32_t) * newdeg[i]);
+            w += newdeg[i];
+        }
+        rowptr[n] = w;
+    }
+    *nnz_out = rowptr[n];
+    *rowptr_out = rowptr;
+    *colids_out = colids;
+    return F2V_OK;
+}
+
+extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint64_t** rowptr_out,
+                            uint32_t** colids_out) {
+    if (!path || !n_out || !nnz_out || !rowptr_out || !colids_out) return F2V_ERR_ARG;
+    FILE* f = fopen(path, "rb");
+    if (!f) return F2V_ERR_ARG;
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return F2V_ERR_ARG; }
+    fclose(f);
+    buf[sz] = 0;
+    const char* p = buf.data();
+    const char* end = p + sz;
+    bool symmetric = false;
+    // header / comment lines start with '%' (IO.h:66-75); "symmetric" anywhere in them mirrors
+    while (p < end && *p == '%') {
+        const char* eol = (const char*)memchr(p, '\n', end - p);
+        if (!eol) eol = end;
+        std::string line(p + 1, eol);
+        if (line.find("symmetric") != std::string::npos) symmetric = true;
+        p = eol < end ? eol + 1 : end;
+    }
+    auto parse_u = [&](uint64_t& v) -> bool {
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) p++;
+        if (p >= end || *p < '0' || *p > '9') return false;
+        v = 0;
+        while (p < end && *p >= '0' && *p <= '9') v = v * 10 + (uint64_t)(*p++ - '0');
+        return true;
+    };
+    auto skip_line = [&]() {
+        const char* eol = (const char*)memchr(p, '\n', end - p);
+        p = eol ? eol + 1 : end;
+    };
+    uint64_t m = 0, ncol = 0, cnt = 0;
+    if (!parse_u(m) || !parse_u(ncol) || !parse_u(cnt)) return F2V_ERR_ARG;
+    skip_line();
+    const uint64_t n = std::max(m, ncol);
+    if (n < 1 || n > 0xffffffffull) return F2V_ERR_ARG;
+    std::vector<uint32_t> src, dst;
+    src.reserve(symmetric ? 2 * cnt : cnt);
+    dst.reserve(symmetric ? 2 * cnt : cnt);
+    for (uint64_t k = 0; k < cnt; k++) {
+        while (p < end && (*p == '\n' || *p == '\r')) p++;
+        uint64_t r, c;
+        if (!parse_u(r) || !parse_u(c)) return F2V_ERR_ARG;   // fewer entries than the size line says
+        skip_line();                                           // the value column is never used
+        if (r < 1 || c < 1 || r > n || c > n) return F2V_ERR_ARG;
+        r--; c--;
+        if (symmetric) {
+            if (r == c) continue;                              // self-loops dropped (IO.h:130-134)
+            src.push_back((uint32_t)r); dst.push_back((uint32_t)c);
+            src.push_back((uint32_t)c); dst.push_back((uint32_t)r);   // mirrored (IO.h:122-129)
+        } else {
+            src.push_back((uint32_t)r); dst.push_back((uint32_t)c);
+        }
+    }
+    *n_out = n;
+    return csr_from_pairs(n, src, dst, /*dedupe=*/false, nnz_out, rowptr_out, colids_out);
+}
+
+extern "C" void f2v_free(void* p) { free(p); }
+
+extern "C" int f2v_write_embd(const char* path, const float* X, uint64_t n, uint32_t dim) {
+    if (!path || !X) return F2V_ERR_ARG;
+    FILE* f = fopen(path, "wb");
+    if (!f) return F2V_ERR_ARG;
+    fprintf(f, "%llu %u\n", (unsigned long long)n, dim);
+    // rows are formatted in parallel blocks, written in order; "%.6g" is what ostream << float emits
+    const uint64_t block = 4096;
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    std::vector<std::string> out(nt);
+    for (uint64_t base = 0; base < n; base += block * nt) {
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+        for (int t = 0; t < nt; t++) {
+            std::string& s = out[t];
+            s.clear();
+            uint64_t lo = base + (uint64_t)t * block, hi = std::min(n, lo + block);
+            char tmp[64];
+            for (uint64_t i = lo; i < hi; i++) {
+                int k = snprintf(tmp, sizeof(tmp), "%llu ", (unsigned long long)(i + 1));
+                s.append(tmp, k);
+                const float* row = X + i * dim;
+                for (uint32_t d = 0; d < dim; d++) {
+                    k = snprintf(tmp, sizeof(tmp), "%.6g ", (double)row[d]);
+                    s.append(tmp, k);
+                }
+                s.push_back('\n');
+            }
+        }
+        for (int t = 0; t < nt; t++)
+            if (!out[t].empty()) fwrite(out[t].data(), 1, out[t].size(), f);
+    }
+    int rc = ferror(f) ? F2V_ERR_ARG : F2V_OK;
+    fclose(f);
+    return rc;
+}
+
+extern "C" int f2v_write_mtx(const char* path, uint64_t n, const uint64_t* rowptr, const uint32_t* colids) {
+    if (!path || !rowptr) return F2V_ERR_ARG;
+    FILE* f = fopen(path, "wb");
+    if (!f) return F2V_ERR_ARG;
+    uint64_t cnt = 0;
+    for (uint64_t i = 0; i < n; i++)
+        for (uint64_t e = rowptr[i]; e < rowptr[i + 1]; e++)
+            if (colids[e] < i) cnt++;
+    fprintf(f, "%%%%MatrixMarket matrix coordinate pattern symmetric\n%llu %llu %llu\n",
+            (unsigned long long)n, (unsigned long long)n, (unsigned long long)cnt);
+    std::vector<char> buf;
+    buf.reserve(1 << 22);
+    char tmp[48];
+    for (uint64_t i = 0; i < n; i++) {
+        for (uint64_t e = rowptr[i]; e < rowptr[i + 1]; e++) {
+            if (colids[e] >= i) continue;
+            int k = snprintf(tmp, sizeof(tmp), "%llu %u\n", (unsigned long long)(i + 1), colids[e] + 1);
+            buf.insert(buf.end(), tmp, tmp + k);
+        }
+        if (buf.size() > (1u << 22) - 64) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+    }
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+    int rc = ferror(f) ? F2V_ERR_ARG : F2V_OK;
+    fclose(f);
+    return rc;
+}
+
+// ------------------------------------------------------------------ R-MAT --------------
+static inline uint64_t splitmix(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// Edge k of the R-MAT stream: one quadrant choice per level from a generator keyed by
+// (seed, k), so the edge list is independent of the thread count and is never stored.
+static inline void rmat_edge(int scale, uint64_t seed, uint64_t k, uint32_t& u, uint32_t& v) {
+    uint64_t st = seed * 0xD1B54A32D192ED03ULL + k * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL;
+    uint32_t uu = 0, vv = 0;
+    uint64_t bits = 0;
+    int have = 0;
+    for (int l = 0; l < scale; l++) {
+        if (have == 0) { bits = splitmix(st); have = 2; }
+        const uint32_t r = (uint32_t)bits;
+        bits >>= 32;
+        have--;
+        // thresholds on 2^32: a = .57, a+b = .76, a+b+c = .95
+        uint32_t q = r < 2448131358u ? 0 : (r < 3264175145u ? 1 : (r < 4080218931u ? 2 : 3));
+        uu = (uu << 1) | (q >> 1);
+        vv = (vv << 1) | (q & 1);
+    }
+    u = uu;
+    v = vv;
+}
+
+extern "C" int f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t* n_out, uint64_t* nnz_out,
+                            uint64_t** rowptr_out, uint32_t** colids_out) {
+    if (scale < 2 || scale > 31 || edge_factor < 1 || !n_out || !nnz_out || !rowptr_out || !colids_out)
+        return F2V_ERR_ARG;
+    const uint64_t n = 1ull << scale, m = (uint64_t)edge_factor * n;
+    std::vector<uint32_t> degc(n, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)m; k++) {
+        uint32_t u, v;
+        rmat_edge(scale, seed, (uint64_t)k, u, v);
+        if (u == v) continue;
+        __atomic_fetch_add(&degc[u], 1u, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&degc[v], 1u, __ATOMIC_RELAXED);
+    }
+    uint64_t* rowptr = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
+    if (!rowptr) return F2V_ERR_NOMEM;
+    rowptr[0] = 0;
+    for (uint64_t i = 0; i < n; i++) rowptr[i + 1] = rowptr[i] + degc[i];
+    const uint64_t tot = rowptr[n];
+    uint32_t* colids = (uint32_t*)malloc(sizeof(uint32_t) * (tot ? tot : 1));
+    if (!colids) { free(rowptr); return F2V_ERR_NOMEM; }
+    std::vector<uint64_t> cur(rowptr, rowptr + n);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)m; k++) {
+        uint32_t u, v;
+        rmat_edge(scale, seed, (uint64_t)k, u, v);
+        if (u == v) continue;
+        colids[__atomic_fetch_add(&cur[u], 1ull, __ATOMIC_RELAXED)] = v;
+        colids[__atomic_fetch_add(&cur[v], 1ull, __ATOMIC_RELAXED)] = u;
+    }
+    std::vector<uint64_t>().swap(cur);
+    std::vector<uint64_t> newdeg(n);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        uint32_t* b = colids + rowptr[i];
+        uint32_t* e = colids + rowptr[i + 1];
+        std::sort(b, e);
+        newdeg[i] = (uint64_t)(std::unique(b, e) - b);
+    }
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t r0 = rowptr[i];
+        rowptr[i] = w;
+        if (w != r0) memmove(colids + w, colids + r0, sizeof(uint32_t) * newdeg[i]);
+        w += newdeg[i];
+    }
+    rowptr[n] = w;
+    *n_out = n;
+    *nnz_out = w;
+    *rowptr_out = rowptr;
+    *colids_out = colids;
+    return F2V_OK;
+}
+
+// ------------------------------------------------------------------ plan ---------------
+extern "C" int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64_t nrows, uint32_t batch,
+                              uint32_t chunk, int walk, int rank, int world, uint64_t* nb,
+                              uint64_t** item_ptr, uint32_t** n_hub, void** items, void** hub) {
+    if (!rowptr || !nb || !item_ptr || !n_hub || !items || !hub || batch == 0 || world < 1 || rank < 0 ||
+        rank >= world || chunk == 0)
+        return F2V_ERR_ARG;
+    f2v::HostPlan hp;
+    f2v::build_host_plan(rowptr, first_row, nrows, batch, chunk, walk != 0, rank, world, hp);
+    const size_t total = hp.item_ptr[hp.nb];
+    *nb = hp.nb;
+    *item_ptr = (uint64_t*)malloc(sizeof(uint64_t) * (hp.nb + 1));
+    *n_hub = (uint32_t*)malloc(sizeof(uint32_t) * (hp.nb ? hp.nb : 1));
+    *items = malloc(sizeof(f2v::Item) * (total ? total : 1));
+    *hub = malloc(sizeof(f2v::HubInfo) * (total ? total : 1));
+    if (!*item_ptr || !*n_hub || !*items || !*hub) return F2V_ERR_NOMEM;
+    memcpy(*item_ptr, hp.item_ptr.data(), sizeof(uint64_t) * (hp.nb + 1));
+    if (hp.nb) memcpy(*n_hub, hp.n_hub.data(), sizeof(uint32_t) * hp.nb);
+    if (total) {
+        memcpy(*items, hp.items.data(), sizeof(f2v::Item) * total);
+        memcpy(*hub, hp.hub.data(), sizeof(f2v::HubInfo) * total);
+    }
+    return F2V_OK;
+}
+
+// ------------------------------------------------------------------ driver -------------
+extern "C" int f2v_train(const f2v_train_args* a, float* X_out, double* seconds) {
+    if (!a || !X_out || !a->rowptr) return F2V_ERR_ARG;
+    if (a->option != F2V_TDIST && a->option != F2V_SIGMOID && a->option != F2V_WALK) return F2V_ERR_ARG;
+    const int model = a->option;
+    const int bs = model == F2V_WALK ? 0 : (a->bs ? 1 : 0);   // -bs ignored by option 7
+    f2v_engine* e = nullptr;
+    int rc = f2v_create(&e, a->device, a->n, a->nnz, a->rowptr, a->colids, a->dim);
+    if (rc) return rc;
+    struct Guard { f2v_engine* e; f2v_rng* g; void* p0; void* p1; void* w;
+                   ~Guard() { f2v_host_free(p0); f2v_host_free(p1); f2v_host_free(w); f2v_rng_destroy(g); f2v_destroy(e); } } gd{e, nullptr, nullptr, nullptr, nullptr};
+    if (a->epoch_mode) { rc = f2v_set_epoch_mode(e, a->epoch_mode); if (rc) return rc; }
+    auto t0 = std::chrono::steady_clock::now();      // algorithms.cpp:557 -- the timer starts before init
+    f2v_rng* g = gd.g = f2v_rng_create(a->seed);
+    if (!g) return F2V_ERR_NOMEM;
+    f2v_init_embeddings(g, model, a->n, a->dim, X_out);
+    rc = f2v_set_embeddings(e, X_out);
+    if (rc) return rc;
+    if (model != F2V_TDIST) {
+        float lut[F2V_LUT_SIZE];
+        f2v_build_lut(lut);
+        rc = f2v_set_lut(e, lut, F2V_LUT_SIZE);
+        if (rc) return rc;
+    }
+    const uint64_t slen = f2v_neg_stream_len(model, a->n, a->batch, a->nsamples, bs);
+    uint32_t* negbuf[2] = {nullptr, nullptr};
+    rc = f2v_host_alloc(&gd.p0, sizeof(uint32_t) * (slen ? slen : 1)); if (rc) return rc;
+    rc = f2v_host_alloc(&gd.p1, sizeof(uint32_t) * (slen ? slen : 1)); if (rc) return rc;
+    negbuf[0] = (uint32_t*)gd.p0; negbuf[1] = (uint32_t*)gd.p1;
+    uint32_t* walks = nullptr;
+    const bool host_walks = model == F2V_WALK && a->walk_sampler == 0;
+    if (host_walks) {
+        rc = f2v_host_alloc(&gd.w, sizeof(uint32_t) * a->n * F2V_WALKLEN); if (rc) return rc;
+        walks = (uint32_t*)gd.w;
+    }
+    // Per epoch the reference draws (walks, then) negatives from the serial stream; the draws
+    // for epoch it+1 are produced on the host while the GPU runs epoch it.
+    auto draw = [&](uint32_t it) -> int {
+        (void)it;
+        if (host_walks) { int r = f2v_draw_walks(g, a->n, a->nnz, a->rowptr, a->colids, walks); if (r) return r; }
+        return f2v_draw_epoch_negatives(g, model, a->n, a->batch, a->nsamples, bs, negbuf[it & 1]);
+    };
+    if (a->iterations > 0) { rc = draw(0); if (rc) return rc; }
+    for (uint32_t it = 0; it < a->iterations; it++) {
+        if (model == F2V_WALK) {
+            if (host_walks) rc = f2v_set_walks(e, walks);
+            else rc = f2v_sample_walks(e, a->seed, it);
+            if (rc) return rc;
+        }
+        rc = f2v_set_negatives(e, negbuf[it & 1], slen);
+        if (rc) return rc;
+        if (host_walks) { rc = f2v_sync(e); if (rc) return rc; }   // walks buffer is reused by the next draw
+        rc = f2v_run_epoch(e, model, a->batch, a->nsamples, bs, a->lr, a->chunk);
+        if (rc) return rc;
+        if (it + 1 < a->iterations) { rc = draw(it + 1); if (rc) return rc; }
+        rc = f2v_sync(e);
+        if (rc) return rc;
+    }
+    rc = f2v_get_embeddings(e, X_out);
+    if (rc) return rc;
+    auto t1 = std::chrono::steady_clock::now();      // algorithms.cpp:647 -- before the file write
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return F2V_OK;
+}
+
+// ------------------------------------------------------------------ C++ mirror ---------
+namespace f2v {
+
+bool SetInputMatricesAsCSR(Csr& A, const std::string& path, std::string* err) {
+    std::cout << "Reading input matrices in text (ascii)... " << std::endl;
+    std::cout << "Input File Directory:" << path << std::endl;
+    uint64_t n = 0, nnz = 0;
+    uint64_t* rp = nullptr;
+    uint32_t* ci = nullptr;
+    int rc = f2v_load_mtx(path.c_str(), &n, &nnz, &rp, &ci);
+    if (rc) {
+        if (err) *err = "cannot read MatrixMarket file " + path;
+        return false;
+    }
+    A.rows = n;
+    A.nnz = nnz;
+    A.rowptr.assign(rp, rp + n + 1);
+    A.colids.assign(ci, ci + nnz);
+    f2v_free(rp);
+    f2v_free(ci);
+    printf("Input Matrix: Rows = %llu, Columns= %llu, nnz = %llu\n", (unsigned long long)n,
+           (unsigned long long)n, (unsigned long long)nnz);
+    return true;
+}
+
+algorithms::algorithms(const Csr& A_csr, std::string input, std::string outputd, uint32_t dim, float gm, uint32_t)
+    : graph(A_csr), GAMMA(gm), DIM(dim), filename(std::move(input)), outputdir(std::move(outputd)) {
+    nCoordinates.assign((size_t)graph.rows * dim, 0.f);
+}
+
+std::vector<float> algorithms::run(int option, int bs, uint32_t iters, uint32_t batch, uint32_t ns, float lr,
+                                   const char* banner, const std::string& tag) {
+    f2v_train_args a{};
+    a.n = graph.rows; a.nnz = graph.nnz; a.rowptr = graph.rowptr.data(); a.colids = graph.colids.data();
+    a.dim = DIM; a.option = option; a.bs = bs; a.iterations = iters; a.batch = batch; a.nsamples = ns;
+    a.lr = lr; a.seed = seed; a.device = device; a.walk_sampler = walk_sampler; a.epoch_mode = epoch_mode;
+    double sec = 0;
+    int rc = f2v_train(&a, nCoordinates.data(), &sec);
+    if (rc != F2V_OK) {
+        // the reference's error convention: message + exit(1) (Test/Force2Vec.cpp:119,186)
+        fprintf(stderr, "Force2Vec GPU engine error %d: %s\n", rc, f2v_last_error());
+        exit(1);
+    }
+    std::cout << banner << sec << " seconds" << std::endl;
+    writeToFile(tag + std::to_string(batch) + "D" + std::to_string(DIM) + "IT" + std::to_string(iters) + "NS" + std::to_string(ns));
+    return std::vector<float>{(float)sec};
+}
+
+std::vector<float> algorithms::AlgoForce2VecNS(uint32_t IT, uint32_t, uint32_t B, uint32_t ns, float lr) {
+    return run(F2V_TDIST, 0, IT, B, ns, lr, "Force2Vec Parallel Wall time required:", "F2VNS");
+}
+std::vector<float> algorithms::AlgoForce2VecNSBS(uint32_t IT, uint32_t, uint32_t B, uint32_t ns, float lr) {
+    return run(F2V_TDIST, 1, IT, B, ns, lr, "Force2Vec Parallel Wall time required (with BS negative samples):", "F2VNS");
+}
+std::vector<float> algorithms::AlgoForce2VecNSRW(uint32_t IT, uint32_t, uint32_t B, uint32_t ns, float lr) {
+    return run(F2V_SIGMOID, 0, IT, B, ns, lr, "Force2Vec Parallel Wall time required:", "F2VWNS");
+}
+std::vector<float> algorithms::AlgoForce2VecNSRWBS(uint32_t IT, uint32_t, uint32_t B, uint32_t ns, float lr) {
+    return run(F2V_SIGMOID, 1, IT, B, ns, lr, "Force2Vec Parallel Wall time required (with BS negative samples):", "F2VWNS");
+}
+std::vector<float> algorithms::AlgoForce2VecNSRWEFF(uint32_t IT, uint32_t, uint32_t B, uint32_t ns, float lr) {
+    return run(F2V_WALK, 0, IT, B, ns, lr, "Force2VecWNSEFF Parallel Wall time required:", "F2VWNSF");
+}
+
+void algorithms::writeToFile(std::string f) {
+    size_t pos = filename.find_last_of('/');
+    std::string lasttok = pos == std::string::npos ? filename : filename.substr(pos + 1);
+    filename = outputdir + lasttok + f + ".embd";
+    std::cout << "Creating output file in following directory:" << filename << std::endl;
+    f2v_write_embd(filename.c_str(), nCoordinates.data(), graph.rows, DIM);
+}
+
+}  // namespace f2v

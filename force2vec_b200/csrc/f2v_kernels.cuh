@@ -1,0 +1,419 @@
+// force2vec_b200/csrc/f2v_kernels.cuh -- sm_100a device code of the Force2Vec force step.
+//
+// One warp owns one work item: a vertex of the minibatch (or, for hub rows, one chunk of a
+// vertex's CSR row).  It walks the item's neighbour indices, gathers the neighbour embedding
+// rows as coalesced float4 (a d=128 row is one 512-B warp transaction, a d=64 row half a
+// warp so two neighbours ride in one instruction), reduces each pair's squared distance /
+// dot product with warp shuffles, turns it into the t-distribution or LUT-sigmoid scalar and
+// applies the learning-rate-scaled update in registers.  The minibatch's shared negative
+// rows (bs=0) are staged once per CTA in shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier -> SASS UBLKCP); per-vertex negatives (bs=1) are gathered like
+// neighbours.  No tensor cores: the work is a sparse gather with ~3 flop/byte.
+//
+// Reference semantics restated here (file:line into /root/reference/sample/algorithms.cpp):
+//   t-dist pair     :598-613 / :614-627     sigmoid pair  :854-868 / :898-911
+//   walk pair       :1154-1170              fast_SM       :766-770      scale  :6-10
+// Jacobi rule (reads see the pre-minibatch table, :588-639): rows < `split` are read from
+// Xlo, rows >= split from Xhi, outputs go to `out`; the epoch driver ping-pongs two tables
+// (Xlo = out = next table, Xhi = current table, split = first row of the minibatch), the
+// single-step driver passes Xlo = Xhi = table and a staging buffer as `out`.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "f2v_plan.hpp"
+
+namespace f2v {
+
+constexpr int kTDist = 5, kSigmoid = 6, kWalk = 7;
+constexpr int kWalkLen = 5;
+constexpr int kLutSize = 2048;
+constexpr int kLutAlloc = 2052;          // padded to a multiple of 16 bytes
+constexpr int kWarpsPerCta = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct BatchParams {
+    const Item* items;
+    const HubInfo* hub;
+    uint32_t n_items;
+    uint32_t n_hub;
+    uint64_t lo;          // first row of the minibatch (bs=1 window origin)
+    uint64_t split;       // rows < split are read from Xlo, others from Xhi
+    const float* Xlo;
+    const float* Xhi;
+    float* out;
+    uint64_t out_base;    // out row of vertex v = out + (v - out_base) * dim
+    const uint32_t* colids;
+    const uint32_t* neg;  // this minibatch's negative indices
+    const uint32_t* walks;
+    const float* lut;
+    float* partials;
+    uint32_t* counters;
+    uint32_t s;
+    uint32_t dim;
+    int bs_mode;
+    int neg_in_smem;
+    float lr;
+};
+
+// ------------------------------------------------------------------ PTX helpers --------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// ------------------------------------------------------------------ row layouts --------
+// VecL<D>: D a multiple of 4 with D/4 in {8,16,32,64}: LPR lanes share a row, each lane
+// holds VPL float4.  RPW rows are in flight per warp instruction.
+template <int D>
+struct VecL {
+    static constexpr int V4 = D / 4;
+    static constexpr int LPR = V4 < 32 ? V4 : 32;
+    static constexpr int RPW = 32 / LPR;
+    static constexpr int VPL = V4 / LPR;
+    static constexpr int NE = 4 * VPL;
+    static constexpr int U = VPL >= 2 ? 4 : 8;
+    static constexpr bool kBulk = true;
+    __device__ static __forceinline__ size_t stride(uint32_t) { return D; }
+    __device__ static __forceinline__ void load_g(float (&f)[NE], const float* row, int l, uint32_t) {
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            float4 t = __ldcg(reinterpret_cast<const float4*>(row) + k * LPR + l);
+            f[4 * k + 0] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
+        }
+    }
+    __device__ static __forceinline__ void load_s(float (&f)[NE], const float* row, int l, uint32_t) {
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            float4 t = *(reinterpret_cast<const float4*>(row) + k * LPR + l);
+            f[4 * k + 0] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
+        }
+    }
+    __device__ static __forceinline__ void store_g(float* row, const float (&f)[NE], int l, uint32_t) {
+#pragma unroll
+        for (int k = 0; k < VPL; k++)
+            __stcg(reinterpret_cast<float4*>(row) + k * LPR + l,
+                   make_float4(f[4 * k + 0], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
+    }
+};
+
+// GenL<NV>: any dim <= 32*NV; lane l holds elements l, l+32, ... (scalar, still coalesced).
+template <int NV>
+struct GenL {
+    static constexpr int LPR = 32;
+    static constexpr int RPW = 1;
+    static constexpr int NE = NV;
+    static constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
+    static constexpr bool kBulk = false;
+    __device__ static __forceinline__ size_t stride(uint32_t dim) { return dim; }
+    __device__ static __forceinline__ void load_g(float (&f)[NE], const float* row, int l, uint32_t dim) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t e = k * 32 + l;
+            f[k] = e < dim ? __ldcg(row + e) : 0.f;
+        }
+    }
+    __device__ static __forceinline__ void load_s(float (&f)[NE], const float* row, int l, uint32_t dim) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t e = k * 32 + l;
+            f[k] = e < dim ? row[e] : 0.f;
+        }
+    }
+    __device__ static __forceinline__ void store_g(float* row, const float (&f)[NE], int l, uint32_t dim) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t e = k * 32 + l;
+            if (e < dim) __stcg(row + e, f[k]);
+        }
+    }
+};
+
+// ------------------------------------------------------------------ scalar pieces ------
+// scale(), algorithms.cpp:6-10 as compiled by the reference (-ffast-math: maxss/minss):
+// NaN -> -MAXBOUND.  CUDA fmaxf/fminf return the non-NaN operand, which gives the same.
+__device__ __forceinline__ float clamp5(float v) { return fminf(fmaxf(v, -5.0f), 5.0f); }
+
+// fast_SM(), algorithms.cpp:766-770; sum and product in double, truncation, no interpolation.
+__device__ __forceinline__ float fast_sm(const float* __restrict__ lut, float v) {
+    if (v > 6.0f) return 1.0f;
+    if (v < -6.0f) return 0.0f;
+    const double res = (double)(float)(kLutSize / 12.0);   // SM_RESOLUTION, algorithms.h:49
+    int i = (int)(((double)v + 6.0) * res);
+    return __ldg(lut + i);
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+    for (int off = LPR / 2; off >= 1; off >>= 1) x += __shfl_xor_sync(kFull, x, off);
+    return x;
+}
+
+// One (i, p) pair.  ATTR: attractive (neighbour / walk sample) or repulsive (negative).
+template <class L, int MODEL, bool ATTR>
+__device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&xi)[L::NE],
+                                            const float (&xp)[L::NE], bool valid, float lr, float sd,
+                                            const float* __restrict__ lut) {
+    if (MODEL == kTDist) {
+        float d[L::NE];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < L::NE; k++) {
+            d[k] = __fsub_rn(xi[k], xp[k]);
+            ss = fmaf(d[k], d[k], ss);
+        }
+        ss = group_sum<L::LPR>(ss);
+        // algorithms.cpp:608 d1 = -2.0/(1.0+attrc);  :622 d1 = 2.0/(repuls*(1.0+repuls))
+        float d1 = ATTR ? __fdiv_rn(-2.0f, __fadd_rn(1.0f, ss))
+                        : __fdiv_rn(2.0f, __fmul_rn(ss, __fadd_rn(1.0f, ss)));
+        float w = valid ? lr : 0.f;
+#pragma unroll
+        for (int k = 0; k < L::NE; k++)
+            acc[k] = __fadd_rn(acc[k], __fmul_rn(w, clamp5(__fmul_rn(d[k], d1))));
+    } else {
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < L::NE; k++) dot = fmaf(xi[k], xp[k], dot);
+        dot = group_sum<L::LPR>(dot);
+        float sg = fast_sm(lut, dot);
+        if (ATTR) {
+            // algorithms.cpp:866  prev += STEP*degi*(1.0-d1)*x_j   (double intermediate)
+            float c = (float)((double)sd * (1.0 - (double)sg));
+            c = valid ? c : 0.f;
+#pragma unroll
+            for (int k = 0; k < L::NE; k++) acc[k] = fmaf(c, xp[k], acc[k]);
+        } else {
+            // algorithms.cpp:908  prev -= STEP*d1*sample   (float)
+            float c = valid ? __fmul_rn(lr, sg) : 0.f;
+#pragma unroll
+            for (int k = 0; k < L::NE; k++) acc[k] = __fsub_rn(acc[k], __fmul_rn(c, xp[k]));
+        }
+    }
+}
+
+// Gather `cnt` rows named by idx[0..cnt) and fold them into acc.  Indices are fetched 32 at
+// a time (one coalesced load) and broadcast by shuffle; U*RPW row loads are in flight.
+template <class L, int MODEL, bool ATTR>
+__device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
+                                             const uint32_t* __restrict__ idx, uint32_t cnt,
+                                             uint32_t self, const BatchParams& p, float sd, int lane) {
+    constexpr int LPR = L::LPR, RPW = L::RPW, U = L::U;
+    const int sub = lane / LPR, l = lane % LPR;
+    const size_t rs = L::stride(p.dim);
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t nb = min(32u, cnt - base);
+        const uint32_t mine = (uint32_t)lane < nb ? __ldg(idx + base + lane) : self;
+        for (uint32_t t0 = 0; t0 * RPW < nb; t0 += U) {
+            float rows[U][L::NE];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t slot = (t0 + u) * RPW + sub;
+                const uint32_t j = __shfl_sync(kFull, mine, slot & 31);
+                valid[u] = slot < nb;
+                if (valid[u]) {
+                    const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
+                    L::load_g(rows[u], src, l, p.dim);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < L::NE; k++) rows[u][k] = xi[k];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                pair_update<L, MODEL, ATTR>(acc, xi, rows[u], valid[u], p.lr, sd, p.lut);
+        }
+    }
+}
+
+template <class L>
+__device__ __forceinline__ void sum_subgroups(float (&acc)[L::NE]) {
+    if (L::RPW > 1) {
+#pragma unroll
+        for (int off = 16; off >= L::LPR; off >>= 1)
+#pragma unroll
+            for (int k = 0; k < L::NE; k++) acc[k] += __shfl_xor_sync(kFull, acc[k], off);
+    }
+}
+
+// One work item.  s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
+template <class L, int MODEL>
+__device__ __forceinline__ void process_item(const BatchParams& p, uint32_t t, const float* s_neg,
+                                             uint64_t* neg_bar, uint32_t neg_parity, int lane) {
+    constexpr int NE = L::NE;
+    const int sub = lane / L::LPR, l = lane % L::LPR;
+    const size_t rs = L::stride(p.dim);
+    const Item it = p.items[t];
+    const bool is_chunk = (it.len & kChunkFlag) != 0;
+    const uint32_t len = it.len & ~kChunkFlag;
+    const uint32_t v = it.v;
+    float xi[NE];
+    L::load_g(xi, ((uint64_t)v < p.split ? p.Xlo : p.Xhi) + (size_t)v * rs, l, p.dim);
+    uint32_t deg = len;
+    HubInfo h{0, 1, 0, 0};
+    if (is_chunk) { h = p.hub[t]; deg = h.deg; }
+    float sd = 0.f;
+    if (MODEL != kTDist) {
+        // degi = 1.0/(deg+1) stored to float (algorithms.cpp:852,1159); STEP*degi in float
+        float degi = (float)(1.0 / (double)(deg + 1u));
+        sd = __fmul_rn(p.lr, degi);
+    }
+    // opt 6/7 accumulate onto y = x_i (algorithms.cpp:824-831); opt 5 onto 0 (:559-567)
+    const bool start_at_xi = (MODEL != kTDist) && !is_chunk && sub == 0;
+    float acc[NE];
+#pragma unroll
+    for (int k = 0; k < NE; k++) acc[k] = start_at_xi ? xi[k] : 0.f;
+
+    if (MODEL == kWalk)
+        gather_pairs<L, MODEL, true>(acc, xi, p.walks + (size_t)v * kWalkLen, kWalkLen, v, p, sd, lane);
+    else
+        gather_pairs<L, MODEL, true>(acc, xi, p.colids + it.e0, len, v, p, sd, lane);
+
+    if (is_chunk) {
+        // split row: publish this chunk's partial sum; the last chunk to arrive folds them in
+        // chunk order (deterministic) and finishes the row.
+        sum_subgroups<L>(acc);
+        if (sub == 0) L::store_g(p.partials + (size_t)h.slot * rs, acc, l, p.dim);
+        __threadfence();
+        __syncwarp();
+        uint32_t old = 0;
+        const uint32_t slot0 = h.slot - h.chunk;
+        if (lane == 0) old = atomicAdd(p.counters + slot0, 1u);
+        old = __shfl_sync(kFull, old, 0);
+        if (old != h.nchunks - 1) return;
+        __threadfence();
+        if (lane == 0) p.counters[slot0] = 0;   // every chunk has arrived: re-arm for the next minibatch
+#pragma unroll
+        for (int k = 0; k < NE; k++) acc[k] = 0.f;
+        if (sub == 0) {
+            for (uint32_t c = 0; c < h.nchunks; c++) {
+                float part[NE];
+                L::load_g(part, p.partials + (size_t)(slot0 + c) * rs, l, p.dim);
+#pragma unroll
+                for (int k = 0; k < NE; k++) acc[k] += part[k];
+            }
+        }
+    }
+
+    // repulsive part: s negatives (algorithms.cpp:614-627, 898-911, 1172-1183)
+    if (s_neg != nullptr) {
+        mbar_wait(neg_bar, neg_parity);
+        for (uint32_t q0 = 0; q0 < p.s; q0 += L::RPW) {
+            const uint32_t q = q0 + sub;
+            const bool valid = q < p.s;
+            float row[NE];
+            if (valid) L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
+            else {
+#pragma unroll
+                for (int k = 0; k < NE; k++) row[k] = xi[k];
+            }
+            pair_update<L, MODEL, false>(acc, xi, row, valid, p.lr, sd, p.lut);
+        }
+    } else {
+        const uint32_t* nidx = p.neg + (p.bs_mode ? (size_t)((uint64_t)v - p.lo) : 0);
+        gather_pairs<L, MODEL, false>(acc, xi, nidx, p.s, v, p, sd, lane);
+    }
+    sum_subgroups<L>(acc);
+    if (sub == 0) {
+        if (MODEL == kTDist || is_chunk) {
+#pragma unroll
+            for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(xi[k], acc[k]);   // X[i] += delta (:629-639)
+        }
+        L::store_g(p.out + (size_t)((uint64_t)v - p.out_base) * rs, acc, l, p.dim);
+    }
+}
+
+// Stage the minibatch's s shared negative rows in shared memory (TMA bulk copies issued by
+// lanes 0..s-1 of warp 0, completion on one mbarrier).
+template <class L>
+__device__ __forceinline__ void stage_negatives(const BatchParams& p, float* s_neg, uint64_t* bar) {
+    const size_t rs = L::stride(p.dim);
+    const uint32_t row_bytes = (uint32_t)(rs * sizeof(float));
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) mbar_expect_tx(bar, row_bytes * p.s);
+        __syncwarp();
+        for (uint32_t q = threadIdx.x; q < p.s; q += 32) {
+            const uint32_t j = __ldg(p.neg + q);
+            const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
+            bulk_g2s(s_neg + (size_t)q * rs, src, row_bytes, bar);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ kernels ------------
+// One launch per minibatch; one warp per item; the hardware CTA scheduler balances the load
+// (items are ordered hub chunks first, then rows by descending degree class).
+template <class L, int MODEL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+force_batch_kernel(const BatchParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* s_neg = nullptr;
+    if (L::kBulk && p.neg_in_smem) {
+        s_neg = reinterpret_cast<float*>(smem_raw + 128);
+        if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        stage_negatives<L>(p, s_neg, bar);
+    }
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (t < p.n_items) process_item<L, MODEL>(p, t, s_neg, bar, 0, lane);
+    // the CTA's shared memory must stay allocated until the bulk copies have landed
+    if (s_neg != nullptr) mbar_wait(bar, 0);
+}
+
+// Counter-based draw for the device walk sampler (host mirror: oracle f2vo_counter_rand).
+__host__ __device__ __forceinline__ uint32_t counter_rand(uint64_t seed, uint64_t epoch, uint64_t vertex, uint32_t step) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (vertex * 8u + step + 1u) + 0xD1B54A32D192ED03ULL * (epoch + 1u);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 33);
+}
+
+// Semi-random walks, one thread per start vertex (rule of algorithms.cpp:1097-1118).
+__global__ void walk_kernel(uint64_t n, uint64_t nnz, const uint64_t* __restrict__ rowptr,
+                            const uint32_t* __restrict__ colids, uint32_t* __restrict__ walks,
+                            uint64_t seed, uint64_t epoch) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t w = i;
+#pragma unroll
+    for (int l = 0; l < kWalkLen; l++) {
+        const uint64_t r0 = __ldg(rowptr + w), r1 = __ldg(rowptr + w + 1);
+        const uint64_t dg = r1 - r0;
+        uint64_t e = w;                       // vertex id used as an edge index (reference quirk)
+        if (dg > 2) e = r0 + counter_rand(seed, epoch, i, (uint32_t)l) % (uint32_t)(dg - 1);
+        else if (dg == 2) e = r0;
+        const uint32_t nx = e < nnz ? __ldg(colids + e) : (uint32_t)w;
+        walks[i * kWalkLen + l] = nx;
+        w = nx;
+    }
+}
+
+}  // namespace f2v

@@ -1,0 +1,145 @@
+/* include/f2v.h -- C ABI of the B200-native Force2Vec force-step engine (libf2v.so).
+ *
+ * The reference (HipGraph/Force2Vec) has no FFI/plugin interface; its only entry
+ * points for this path are the C++ methods
+ *     vector<float> algorithms::AlgoForce2VecNS | NSBS | NSRW | NSRWBS | NSRWEFF
+ *         (INDEXTYPE ITERATIONS, INDEXTYPE NUMOFTHREADS, INDEXTYPE BATCHSIZE,
+ *          INDEXTYPE ns, VALUETYPE lr)                  sample/algorithms.h:86-90
+ * operating on `graph` (CSR) and `nCoordinates` (row-major n x DIM fp32,
+ * sample/algorithms.h:53-54,68), and the unused per-vertex generator signature
+ * sample/kgen/genDimFrc.base:36-57.  The functions below are what a C++ host that
+ * replaces those method bodies binds; each one cites the
+ * reference lines whose work it takes over.
+ *
+ * Conventions: plain pointers and sizes only; every function returns F2V_OK (0) or a
+ * negative F2V_ERR_*; the message is available from f2v_last_error() (thread-local).
+ * No exceptions cross the boundary.  The caller owns every host buffer; the library
+ * owns all device memory.  One host thread drives one engine (one GPU).  There is no
+ * CPU fallback: without a usable CUDA device every compute call fails with
+ * F2V_ERR_CUDA.
+ */
+#ifndef F2V_H
+#define F2V_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F2V_ABI_VERSION 1
+
+/* model ids = the reference CLI's -option values (Test/Force2Vec.cpp:139-150) */
+#define F2V_TDIST   5   /* tForce2Vec: algorithms.cpp:544-652 (bs=0), 654-753 (bs=1)  */
+#define F2V_SIGMOID 6   /* sForce2Vec: algorithms.cpp:778-932 (bs=0), 934-1060 (bs=1) */
+#define F2V_WALK    7   /* rForce2Vec: algorithms.cpp:1063-1203                        */
+#define F2V_WALKLEN 5   /* WALKLENGTH, algorithms.cpp:1074                             */
+#define F2V_LUT_SIZE 2048 /* SM_TABLE_SIZE, algorithms.h:43                            */
+
+#define F2V_OK          0
+#define F2V_ERR_ARG    -1
+#define F2V_ERR_CUDA   -2
+#define F2V_ERR_NCCL   -3
+#define F2V_ERR_STATE  -4
+#define F2V_ERR_NOMEM  -5
+
+typedef struct f2v_engine f2v_engine;
+
+const char* f2v_last_error(void);
+int  f2v_abi_version(void);
+/* number of CUDA devices visible, or a negative error (no driver / no GPU) */
+int  f2v_device_count(void);
+
+/* ---- lifetime --------------------------------------------------------------------
+ * f2v_create replaces the `algorithms` constructor (algorithms.h:60-70): it takes the
+ * CSR (rowptr u64[n+1], colids u32[nnz], ascending within a row as CSR.h:154-186
+ * produces) and uploads it to device `device_id`; the n x dim embedding table is
+ * allocated on the device.  dim: any value >= 1 (fast paths for 32/64/128/256).      */
+int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz,
+               const uint64_t* rowptr, const uint32_t* colids, uint32_t dim);
+int f2v_destroy(f2v_engine* e);
+/* Run on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the
+ * engine's own stream.  Pass NULL to go back to the engine's stream.                 */
+int f2v_set_stream(f2v_engine* e, void* cuda_stream);
+int f2v_sync(f2v_engine* e);
+
+/* Page-locked host memory for the buffers handed to the calls below (copies from
+ * pageable memory work too, at lower PCIe throughput).                               */
+int f2v_host_alloc(void** p, uint64_t bytes);
+int f2v_host_free(void* p);
+
+/* ---- state -----------------------------------------------------------------------
+ * nCoordinates in / out (algorithms.h:54).  Host buffers of n*dim floats, row-major. */
+int f2v_set_embeddings(f2v_engine* e, const float* X_host);
+int f2v_get_embeddings(f2v_engine* e, float* X_host);
+int f2v_get_rows(f2v_engine* e, uint64_t first_row, uint64_t nrows, float* rows_host);
+/* The sigmoid table built on the host with the reference expression
+ * (init_SM_TABLE, algorithms.cpp:757-764): `count` = 2048 entries; entry 2048 (the
+ * reference's out-of-bounds read for v == 6.0f exactly) is defined as 1.0f.          */
+int f2v_set_lut(f2v_engine* e, const float* sm_table, uint32_t count);
+
+/* ---- sample streams (made resident on the device) -----------------------------------
+ * Negative indices for the coming step/epoch, in the order the reference draws them
+ * (randIndex, algorithms.cpp:55-58 at :578,:687,:816,:967,:1126).  Layout per
+ * minibatch b with stride W:  bs_mode 0 (and model 7): W = s;  bs_mode 1: W = batch+s-1
+ * -- the first batch+s-1 of the reference's s*batch draws, the only ones it reads
+ * (vertex k uses entries k..k+s-1, algorithms.cpp:719-720,1029-1030).                 */
+int f2v_set_negatives(f2v_engine* e, const uint32_t* idx_host, uint64_t count);
+/* Several epochs' streams may be uploaded at once; the next f2v_run_epoch reads the
+ * resident stream from entry `offset` on (f2v_set_negatives resets it to 0).            */
+int f2v_set_negative_offset(f2v_engine* e, uint64_t offset);
+/* Walk samples, n*5 u32 (walksamples, algorithms.cpp:1075,1097-1118).                  */
+int f2v_set_walks(f2v_engine* e, const uint32_t* walks_host);
+int f2v_get_walks(f2v_engine* e, uint32_t* walks_host);
+/* Device semi-random-walk sampler: same rule as algorithms.cpp:1097-1118, but the draw
+ * for (epoch, vertex, step) comes from a counter-based generator (documented in
+ * DESIGN.md; host mirror in oracle/f2v_oracle.c:f2vo_walks_counter) instead of the
+ * serial libc stream, so it is parallel.  Fills the resident walk buffer.             */
+int f2v_sample_walks(f2v_engine* e, uint64_t seed, uint64_t epoch);
+
+/* ---- the hot path ------------------------------------------------------------------
+ * f2v_step: ONE Jacobi minibatch over rows [first_row, first_row+nrows): every read of
+ * X sees the pre-step table, then the rows are replaced (algorithms.cpp:588-639,
+ * 833-921, 1142-1193).  neg_idx_host: s entries (bs_mode 0 / model 7) or nrows+s-1
+ * (bs_mode 1).  walks_host: n*5 or NULL to use the resident walks.  Teacher-forced
+ * entry point used by the parity tests; synchronous.                                  */
+int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows,
+             const uint32_t* neg_idx_host, uint32_t s, int bs_mode, float lr,
+             const uint32_t* walks_host);
+
+/* f2v_run_epoch: one epoch = ceil(n/batch) dependent minibatches over contiguous row
+ * ranges in natural order (algorithms.cpp:569-640), consuming the resident negative
+ * stream (ceil(n/batch)*W entries) and, for model 7, the resident walks.  Same result
+ * as a loop of f2v_step.  Asynchronous on the engine's stream.
+ * chunk: hub rows longer than `chunk` edges are split across warps (0 = default).     */
+int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode,
+                  float lr, uint32_t chunk);
+
+/* Host-buffer epoch (the end-to-end call): upload X_in (nullable = keep resident),
+ * the epoch's negatives and walks (nullable), run the epoch, download into X_out
+ * (nullable).  Synchronous.                                                           */
+int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode,
+                       float lr, uint32_t chunk, const float* X_in,
+                       const uint32_t* neg_idx_host, uint64_t neg_count,
+                       const uint32_t* walks_host, float* X_out);
+
+/* Execution mode of f2v_run_epoch: 0 = one kernel launch per minibatch (default),
+ * 1 = one persistent cooperative kernel per epoch with a grid barrier per minibatch.  */
+int f2v_set_epoch_mode(f2v_engine* e, int mode);
+/* Kernel launches issued by this engine since creation (force + sampler kernels).     */
+uint64_t f2v_launch_count(const f2v_engine* e);
+/* Device time of the last f2v_run_epoch in milliseconds (CUDA events on its stream);
+ * synchronises.                                                                       */
+int f2v_last_epoch_ms(f2v_engine* e, float* ms);
+
+/* ---- multi-GPU (one process per GPU) -----------------------------------------------
+ * Every rank holds a full replica of X and the CSR.  Each minibatch is split into
+ * `world` contiguous slices; a rank updates its slice and the slices are exchanged
+ * with an NCCL all-gather before the next minibatch.  id128: the 128-byte
+ * ncclUniqueId produced by f2v_comm_unique_id on rank 0 and broadcast by the caller.
+ * batch must be a multiple of world.                                                  */
+int f2v_comm_unique_id(void* id128);
+int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F2V_H */

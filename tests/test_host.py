@@ -1,0 +1,225 @@
+"""CPU: host side of the drop-in (libf2v.so, include/f2v_host.h) against the oracle and the
+golden fixtures: rand() stream and samplers, MatrixMarket loader, .embd writer, R-MAT generator,
+work plan; and that the C-ABI library loads, exports every declared symbol and fails loudly
+without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+from conftest import GOLDEN, ROOT
+
+import force2vec_b200 as F
+from force2vec_b200 import host, capi
+
+
+def test_library_exports_every_declared_symbol():
+    L = F.lib()
+    declared = set()
+    for h in ("f2v.h", "f2v_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(f2v_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 40
+    assert set(capi.ENGINE_SYMBOLS + capi.HOST_SYMBOLS) == declared
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert L.f2v_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly(karate):
+    """No CPU fallback: on a box without a usable device, engine creation raises."""
+    if F.lib().f2v_device_count() > 0:
+        pytest.skip("a GPU is present")
+    rp, ci = karate
+    with pytest.raises(F.F2VError):
+        F.Engine(rp, ci, 16)
+    a = F.Algorithms(rp, ci, "karate.mtx", "/tmp/", 16)
+    with pytest.raises(F.F2VError):
+        a.AlgoForce2VecNS(1, 1, 8, 5, 0.02)
+
+
+def test_rand_stream(oracle):
+    want = np.load(os.path.join(GOLDEN, "rand_srand1.npy"))
+    g = host.RandStream(1)
+    assert [g.rand() for _ in range(len(want))] == want.tolist()
+
+
+def test_lut(oracle):
+    assert np.array_equal(host.build_lut(), oracle.build_lut()[:2048])
+    np.testing.assert_allclose(host.build_lut(), np.load(os.path.join(GOLDEN, "ref_lut.npy")), rtol=0, atol=2.4e-7)
+
+
+@pytest.mark.parametrize("name", ["cora.mtx", "karate.mtx"])
+def test_loader_matches_reference_semantics(oracle, name):
+    path = os.path.join(GOLDEN, name)
+    rp, ci = host.load_mtx(path)
+    rp2, ci2 = oracle.load_mtx(path)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    if name == "cora.mtx":
+        assert len(rp) - 1 == 2708 and len(ci) == 10858
+
+
+def test_loader_general_and_symmetric(tmp_path, oracle):
+    # general: entries kept as they are, including self-loops and duplicates, values ignored
+    p = tmp_path / "g.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real general\n% c\n4 4 6\n1 2 0.5\n2 1 3\n3 3 1\n1 2 7\n4 1 1\n2 4 1\n")
+    rp, ci = host.load_mtx(str(p))
+    assert rp.tolist() == [0, 2, 4, 5, 6] and ci.tolist() == [1, 1, 0, 3, 2, 0]
+    rp2, ci2 = oracle.load_mtx(str(p))
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    # symmetric: mirrored, self-loops dropped
+    p = tmp_path / "s.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate pattern symmetric\n4 4 4\n2 1\n3 3\n4 1\n4 2\n")
+    rp, ci = host.load_mtx(str(p))
+    assert rp.tolist() == [0, 2, 4, 4, 6] and ci.tolist() == [1, 3, 0, 3, 0, 1]
+    with pytest.raises(F.F2VError):
+        host.load_mtx(str(tmp_path / "missing.mtx"))
+    p = tmp_path / "bad.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate pattern symmetric\n4 4 3\n2 1\n")
+    with pytest.raises(F.F2VError):
+        host.load_mtx(str(p))
+
+
+@pytest.mark.parametrize("model,bs", [(5, 0), (5, 1), (6, 0), (6, 1), (7, 0)])
+def test_streams_match_oracle(oracle, cora, model, bs):
+    rp, ci = cora
+    n = len(rp) - 1
+    g, o = host.RandStream(1), oracle.Rng(1)
+    assert np.array_equal(g.init_embeddings(model, n, 24), oracle.init_embeddings(o, model, n, 24))
+    B, s = 200, 5
+    nb = (n + B - 1) // B
+    W = (B + s - 1) if (bs and model != 7) else s
+    for _ in range(2):
+        if model == 7:
+            assert np.array_equal(g.walks(rp, ci), oracle.walks(o, rp, ci))
+        neg = g.epoch_negatives(model, n, B, s, bs).reshape(nb, W)
+        for b in range(nb):
+            assert np.array_equal(neg[b], oracle.draw_negatives(o, model, bs, n, B, s, b)[:W])
+    assert g.rand() == o.rand()          # both consumed exactly the same number of draws
+
+
+def test_embd_writer_matches_reference_text(oracle):
+    """Byte-for-byte: re-emitting the values of a reference-written .embd reproduces the file."""
+    for opt in (5, 6, 7):
+        src = os.path.join(GOLDEN, "karate_opt%d.embd" % opt)
+        X = oracle.read_embd(src)
+        out = "/tmp/f2v_test_writer_%d.embd" % os.getpid()
+        host.write_embd(out, X)
+        assert open(out).read() == open(src).read()
+        os.remove(out)
+
+
+def test_embd_writer_format():
+    X = np.array([[1e-5, 123456.789, -0.5, 1.0], [0.1, 2.5e-7, 3.0, -1e10]], np.float32)
+    out = "/tmp/f2v_test_fmt_%d.embd" % os.getpid()
+    host.write_embd(out, X)
+    lines = open(out).read().split("\n")
+    os.remove(out)
+    assert lines[0] == "2 4"
+    assert lines[1] == "1 1e-05 123457 -0.5 1 "          # ostream default precision, trailing space
+    assert lines[2] == "2 0.1 2.5e-07 3 -1e+10 "
+    assert lines[3] == ""
+
+
+def test_rmat_generator():
+    rp, ci = host.rmat_csr(12, 16, 1)
+    n = len(rp) - 1
+    assert n == 4096 and rp[-1] == len(ci)
+    deg = np.diff(rp.astype(np.int64))
+    rows = np.repeat(np.arange(n), deg)
+    assert (rows != ci).all()                                            # no self-loops
+    key = rows.astype(np.int64) * n + ci
+    assert (np.diff(key) > 0).all()                                      # sorted rows, no duplicates
+    assert np.array_equal(np.sort(ci.astype(np.int64) * n + rows), key)  # symmetric
+    rp2, ci2 = host.rmat_csr(12, 16, 1)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)           # deterministic
+    rp3, ci3 = host.rmat_csr(12, 16, 2)
+    assert not np.array_equal(ci, ci3)
+    assert deg.max() > 20 * deg.mean()                                   # skewed
+
+
+def test_rmat_thread_count_independent():
+    code = ("import sys; sys.path.insert(0, %r); from force2vec_b200 import host; import numpy as np;"
+            "rp, ci = host.rmat_csr(11, 8, 5); print(int(rp.sum()), int(ci.astype(np.int64).sum()), len(ci))" % ROOT)
+    outs = []
+    for t in ("1", "4"):
+        env = dict(os.environ, OMP_NUM_THREADS=t)
+        outs.append(subprocess.check_output(["python", "-c", code], env=env).decode())
+    assert outs[0] == outs[1]
+
+
+def test_mtx_roundtrip(tmp_path, oracle):
+    rp, ci = host.rmat_csr(10, 8, 3)
+    p = str(tmp_path / "r.mtx")
+    host.write_mtx(p, rp, ci)
+    a = host.load_mtx(p)
+    b = oracle.load_mtx(p)
+    assert np.array_equal(a[0], rp) and np.array_equal(a[1], ci)
+    assert np.array_equal(b[0], rp) and np.array_equal(b[1], ci)
+
+
+def _check_plan(rp, batch, chunk, world):
+    n = len(rp) - 1
+    deg = np.diff(rp.astype(np.int64))
+    nb = (n + batch - 1) // batch
+    seen_rows = np.zeros(n, np.int64)
+    seen_edges = np.zeros(n, np.int64)
+    for rank in range(world):
+        pl = host.plan_build(rp, batch, chunk, rank=rank, world=world)
+        assert pl["nb"] == nb
+        it, hb = pl["items"], pl["hub"]
+        for b in range(nb):
+            lo, hi = int(pl["item_ptr"][b]), int(pl["item_ptr"][b + 1])
+            items, hubs = it[lo:hi], hb[lo:hi]
+            nh = int(pl["n_hub"][b])
+            flag = (items["len"] & host.CHUNK_FLAG) != 0
+            assert flag[:nh].all() and not flag[nh:].any()              # hub chunks lead the minibatch
+            ln = (items["len"] & 0x7fffffff).astype(np.int64)
+            assert (ln[nh:] <= chunk).all() and (ln[:nh] <= chunk).all()
+            # rank's slice of the minibatch
+            blo, bhi = b * batch, min(n, (b + 1) * batch)
+            sl = batch // world
+            slo = min(blo + rank * sl, bhi) if world > 1 else blo
+            shi = min(slo + sl, bhi) if world > 1 else bhi
+            assert ((items["v"] >= slo) & (items["v"] < shi)).all()
+            # non-hub rows appear once, sorted by descending degree class
+            cls = np.where(ln[nh:] == 0, 0, np.floor(np.log2(np.maximum(ln[nh:], 1))).astype(int) + 1)
+            assert (np.diff(cls) <= 0).all()
+            np.add.at(seen_rows, items["v"][nh:], 1)
+            np.add.at(seen_edges, items["v"], ln)
+            # hub rows: chunks 0..nchunks-1 in order, contiguous edge ranges, distinct slots
+            if nh:
+                hv = items["v"][:nh]
+                for v in np.unique(hv):
+                    m = hv == v
+                    h = hubs[:nh][m]
+                    assert h["chunk"].tolist() == list(range(len(h))) and (h["nchunks"] == len(h)).all()
+                    assert (h["deg"] == deg[v]).all()
+                    e0 = items["e0"][:nh][m].astype(np.int64)
+                    assert e0[0] == rp[v] and np.array_equal(e0[1:], e0[:-1] + ln[:nh][m][:-1])
+                    seen_rows[v] += 1
+                assert len(np.unique(hubs["slot"][:nh])) == nh
+                assert hubs["slot"][:nh].max() < nh
+    assert (seen_rows == 1).all()
+    assert np.array_equal(seen_edges, deg)
+
+
+@pytest.mark.parametrize("batch,chunk,world", [(256, 64, 1), (100, 8, 1), (5000, 16, 1), (256, 64, 2), (96, 8, 4)])
+def test_plan_covers_every_row_once(batch, chunk, world):
+    rp, ci = host.rmat_csr(11, 16, 1)
+    _check_plan(rp, batch, chunk, world)
+
+
+def test_cli_without_gpu_exits_nonzero():
+    if F.lib().f2v_device_count() > 0:
+        pytest.skip("a GPU is present")
+    exe = os.path.join(ROOT, "bin", "Force2Vec")
+    if not os.path.exists(exe):
+        pytest.skip("bin/Force2Vec not built")
+    r = subprocess.run([exe, "-input", os.path.join(GOLDEN, "karate.mtx"), "-output", "/tmp/", "-iter", "1"],
+                       capture_output=True, cwd="/tmp")
+    assert r.returncode == 1 and b"engine error" in r.stderr
+    r = subprocess.run([exe], capture_output=True, cwd="/tmp")
+    assert r.returncode == 1 and b"Valid input file needed" in r.stdout
