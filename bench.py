@@ -132,8 +132,26 @@ def make_graph(a):
 
 
 # ------------------------------------------------------------------------------------------
+class StdoutToStderr:
+    """The reference prints progress on C stdout; keep our stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference(a, rp, ci, epochs, warm):
     """The unmodified reference (oracle/_ref) on this box's host cores.  Returns dict."""
+    with StdoutToStderr():
+        return _cpu_reference(a, rp, ci, epochs, warm)
+
+
+def _cpu_reference(a, rp, ci, epochs, warm):
     from oracle import oracle as O
     n, nnz = len(rp) - 1, len(ci)
     cores = os.cpu_count() or 1
