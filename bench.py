@@ -259,7 +259,12 @@ def run_ours(a):
         g.epoch_negatives(a.model, n, a.batch, a.nsamples, a.bs, out=neg_np[k * stride:(k + 1) * stride])
 
     eng = F.Engine(rp, ci, a.dim, device=local)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    # the engine launches on torch's current stream so that torch.cuda.Event brackets its kernels;
+    # that must be a real (non-default) stream: handle 0 means "engine's own stream" in the C ABI
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    eng.set_stream(stream.cuda_stream)
     if a.mode:
         eng.set_epoch_mode(a.mode)
     if world > 1:
