@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--lr", type=float, default=0.02)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0, help="engine epoch mode (0 per-minibatch launches, 1 persistent)")
+    ap.add_argument("--variant", type=int, default=0, help="d=128 kernel lane layout (f2v_set_option)")
+    ap.add_argument("--neg-smem", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra-batches", default="", help="comma list of additional batch sizes to report")
@@ -267,6 +269,8 @@ def run_ours(a):
     eng.set_stream(stream.cuda_stream)
     if a.mode:
         eng.set_epoch_mode(a.mode)
+    eng.set_option("variant", a.variant)
+    eng.set_option("neg_smem", a.neg_smem)
     if world > 1:
         ids = [F.Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

@@ -13,7 +13,7 @@ ENGINE_SYMBOLS = [
     "f2v_get_embeddings", "f2v_get_rows", "f2v_set_lut", "f2v_set_negatives", "f2v_set_negative_offset",
     "f2v_set_walks",
     "f2v_get_walks", "f2v_sample_walks", "f2v_step", "f2v_run_epoch", "f2v_run_epoch_host",
-    "f2v_set_epoch_mode", "f2v_launch_count", "f2v_last_epoch_ms", "f2v_comm_unique_id",
+    "f2v_set_epoch_mode", "f2v_set_option", "f2v_launch_count", "f2v_last_epoch_ms", "f2v_comm_unique_id",
     "f2v_comm_init",
 ]
 HOST_SYMBOLS = [
@@ -72,6 +72,7 @@ def lib():
     L.f2v_run_epoch.argtypes = [vp, i32, u32, u32, i32, f32, u32]
     L.f2v_run_epoch_host.argtypes = [vp, i32, u32, u32, i32, f32, u32, vp, vp, u64, vp, vp]
     L.f2v_set_epoch_mode.argtypes = [vp, i32]
+    L.f2v_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.f2v_launch_count.argtypes = [vp]
     L.f2v_launch_count.restype = u64
     L.f2v_last_epoch_ms.argtypes = [vp, C.POINTER(f32)]

@@ -111,6 +111,8 @@ struct f2v_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     int epoch_mode = 0;
+    int variant = 0;
+    int neg_smem = 1;
     uint64_t launches = 0;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -185,7 +187,8 @@ static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st) {
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    unsigned grid = (p.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned per_cta = kWarpsPerCta * L::G;
+    unsigned grid = (p.n_items + per_cta - 1) / per_cta;
     force_batch_kernel<L, MODEL><<<grid, kWarpsPerCta * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
@@ -201,10 +204,16 @@ static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t 
 
 static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st) {
     switch (p.dim) {
-    case 32: return launch_batch_m<VecL<32>>(model, p, st);
-    case 64: return launch_batch_m<VecL<64>>(model, p, st);
-    case 128: return launch_batch_m<VecL<128>>(model, p, st);
-    case 256: return launch_batch_m<VecL<256>>(model, p, st);
+    case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st);
+    case 64: return launch_batch_m<VecL<64, 8, 4>>(model, p, st);
+    case 128:
+        switch (p.variant) {
+        case 1: return launch_batch_m<VecL<128, 32, 8>>(model, p, st);
+        case 2: return launch_batch_m<VecL<128, 8, 2>>(model, p, st);
+        case 3: return launch_batch_m<VecL<128, 16, 8>>(model, p, st);
+        default: return launch_batch_m<VecL<128, 16, 4>>(model, p, st);
+        }
+    case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st);
     default: break;
     }
     if (p.dim <= 32) return launch_batch_m<GenL<1>>(model, p, st);
@@ -216,7 +225,7 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
 }
 
 static bool bulk_ok(const f2v_engine* e, uint32_t s, int bs_mode) {
-    if (bs_mode != 0 || s == 0) return false;
+    if (bs_mode != 0 || s == 0 || !e->neg_smem) return false;
     if (!(e->dim == 32 || e->dim == 64 || e->dim == 128 || e->dim == 256)) return false;
     return 128 + (size_t)s * e->dim * sizeof(float) <= 200 * 1024;
 }
@@ -461,7 +470,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     p.colids = e->d_colids; p.neg = e->d_neg; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
-    p.lr = lr;
+    p.lr = lr; p.variant = e->variant;
     CU(launch_batch(model, p, e->stream));
     e->launches++;
     // apply after the join (algorithms.cpp:629-639 / :913-921)
@@ -513,7 +522,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
     p.colids = e->d_colids; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
-    p.lr = lr;
+    p.lr = lr; p.variant = e->variant;
     const uint64_t slice = batch / (uint64_t)e->world;
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
@@ -562,6 +571,14 @@ int f2v_set_epoch_mode(f2v_engine* e, int mode) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
     if (mode != 0) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
     e->epoch_mode = mode;
+    return F2V_OK;
+}
+
+int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
+    if (!e || !name) return fail(F2V_ERR_ARG, "null argument");
+    if (!strcmp(name, "variant")) e->variant = (int)value;
+    else if (!strcmp(name, "neg_smem")) e->neg_smem = value != 0;
+    else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }
 

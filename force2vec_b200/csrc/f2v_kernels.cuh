@@ -52,6 +52,7 @@ struct BatchParams {
     uint32_t dim;
     int bs_mode;
     int neg_in_smem;
+    int variant;          // layout variant of the d=128 kernels (tuning knob)
     float lr;
 };
 
@@ -87,17 +88,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------ row layouts --------
-// VecL<D>: D a multiple of 4 with D/4 in {8,16,32,64}: LPR lanes share a row, each lane
-// holds VPL float4.  RPW rows are in flight per warp instruction.
-template <int D>
+// A warp is cut into G = 32/LPR groups of LPR lanes; every group owns one work item (its own
+// vertex) and gathers that item's rows, U at a time.  VecL<D,LPR>: a row is D/4 float4, lane l
+// of the group holds float4 l, l+LPR, ... (each load instruction covers LPR*16 contiguous
+// bytes of the row: a d=128 row is one 512-B transaction with LPR=32, two 256-B ones with
+// LPR=16).  Smaller LPR = more vertices in flight per warp (latency tolerance on short rows)
+// and fewer redundant per-pair scalar instructions.
+template <int D, int LPR_, int U_>
 struct VecL {
     static constexpr int V4 = D / 4;
-    static constexpr int LPR = V4 < 32 ? V4 : 32;
-    static constexpr int RPW = 32 / LPR;
+    static constexpr int LPR = LPR_;
+    static constexpr int G = 32 / LPR;
     static constexpr int VPL = V4 / LPR;
     static constexpr int NE = 4 * VPL;
-    static constexpr int U = VPL >= 2 ? 4 : 8;
+    static constexpr int U = U_;
     static constexpr bool kBulk = true;
+    static_assert(V4 % LPR == 0 && VPL >= 1 && U <= LPR && LPR % U == 0, "bad layout");
     __device__ static __forceinline__ size_t stride(uint32_t) { return D; }
     __device__ static __forceinline__ void load_g(float (&f)[NE], const float* row, int l, uint32_t) {
 #pragma unroll
@@ -121,11 +127,12 @@ struct VecL {
     }
 };
 
-// GenL<NV>: any dim <= 32*NV; lane l holds elements l, l+32, ... (scalar, still coalesced).
+// GenL<NV>: any dim <= 32*NV; one group per warp, lane l holds elements l, l+32, ... (scalar
+// loads, still coalesced).
 template <int NV>
 struct GenL {
     static constexpr int LPR = 32;
-    static constexpr int RPW = 1;
+    static constexpr int G = 1;
     static constexpr int NE = NV;
     static constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
     static constexpr bool kBulk = false;
@@ -174,7 +181,9 @@ __device__ __forceinline__ float group_sum(float x) {
     return x;
 }
 
-// One (i, p) pair.  ATTR: attractive (neighbour / walk sample) or repulsive (negative).
+// One (i, p) pair of one group.  ATTR: attractive (neighbour / walk sample) or repulsive
+// (negative).  Executed by the whole warp (the reduction shuffles are warp-wide); groups with
+// nothing to do pass valid = false and contribute exactly zero.
 template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&xi)[L::NE],
                                             const float (&xp)[L::NE], bool valid, float lr, float sd,
@@ -216,25 +225,29 @@ __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&x
     }
 }
 
-// Gather `cnt` rows named by idx[0..cnt) and fold them into acc.  Indices are fetched 32 at
-// a time (one coalesced load) and broadcast by shuffle; U*RPW row loads are in flight.
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(kFull, v); }
+
+// Every group gathers its own `cnt` rows named by idx[0..cnt) (in order) and folds them into
+// its acc.  Indices are fetched LPR at a time per group (coalesced) and broadcast inside the
+// group by shuffle; U row loads per group (G*U per warp) are in flight.
 template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const uint32_t* __restrict__ idx, uint32_t cnt,
-                                             uint32_t self, const BatchParams& p, float sd, int lane) {
-    constexpr int LPR = L::LPR, RPW = L::RPW, U = L::U;
-    const int sub = lane / LPR, l = lane % LPR;
+                                             uint32_t self, const BatchParams& p, float sd, int l) {
+    constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
-    for (uint32_t base = 0; base < cnt; base += 32) {
-        const uint32_t nb = min(32u, cnt - base);
-        const uint32_t mine = (uint32_t)lane < nb ? __ldg(idx + base + lane) : self;
-        for (uint32_t t0 = 0; t0 * RPW < nb; t0 += U) {
+    const uint32_t cnt_max = L::G > 1 ? warp_max(cnt) : cnt;
+    for (uint32_t base = 0; base < cnt_max; base += LPR) {
+        const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
+        const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
+        const uint32_t mine = (uint32_t)l < nb ? __ldg(idx + base + l) : self;
+        for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
             bool valid[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const uint32_t slot = (t0 + u) * RPW + sub;
-                const uint32_t j = __shfl_sync(kFull, mine, slot & 31);
+                const uint32_t slot = t0 + u;
+                const uint32_t j = __shfl_sync(kFull, mine, slot, LPR);
                 valid[u] = slot < nb;
                 if (valid[u]) {
                     const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
@@ -251,29 +264,27 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     }
 }
 
-template <class L>
-__device__ __forceinline__ void sum_subgroups(float (&acc)[L::NE]) {
-    if (L::RPW > 1) {
-#pragma unroll
-        for (int off = 16; off >= L::LPR; off >>= 1)
-#pragma unroll
-            for (int k = 0; k < L::NE; k++) acc[k] += __shfl_xor_sync(kFull, acc[k], off);
-    }
-}
-
-// One work item.  s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
+// G work items, one per group: items t_base .. t_base+G-1 (groups past n_items idle).
+// s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
 template <class L, int MODEL>
-__device__ __forceinline__ void process_item(const BatchParams& p, uint32_t t, const float* s_neg,
-                                             uint64_t* neg_bar, uint32_t neg_parity, int lane) {
-    constexpr int NE = L::NE;
-    const int sub = lane / L::LPR, l = lane % L::LPR;
+__device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_base, const float* s_neg,
+                                              uint64_t* neg_bar, uint32_t neg_parity, int lane) {
+    constexpr int NE = L::NE, LPR = L::LPR;
+    const int g = lane / LPR, l = lane % LPR;
     const size_t rs = L::stride(p.dim);
-    const Item it = p.items[t];
+    const uint32_t t = t_base + g;
+    const bool active = t < p.n_items;
+    Item it{0, 0, 0};
+    if (active) it = p.items[t];
     const bool is_chunk = (it.len & kChunkFlag) != 0;
     const uint32_t len = it.len & ~kChunkFlag;
     const uint32_t v = it.v;
     float xi[NE];
-    L::load_g(xi, ((uint64_t)v < p.split ? p.Xlo : p.Xhi) + (size_t)v * rs, l, p.dim);
+    if (active) L::load_g(xi, ((uint64_t)v < p.split ? p.Xlo : p.Xhi) + (size_t)v * rs, l, p.dim);
+    else {
+#pragma unroll
+        for (int k = 0; k < NE; k++) xi[k] = 0.f;
+    }
     uint32_t deg = len;
     HubInfo h{0, 1, 0, 0};
     if (is_chunk) { h = p.hub[t]; deg = h.deg; }
@@ -284,34 +295,46 @@ __device__ __forceinline__ void process_item(const BatchParams& p, uint32_t t, c
         sd = __fmul_rn(p.lr, degi);
     }
     // opt 6/7 accumulate onto y = x_i (algorithms.cpp:824-831); opt 5 onto 0 (:559-567)
-    const bool start_at_xi = (MODEL != kTDist) && !is_chunk && sub == 0;
+    const bool start_at_xi = (MODEL != kTDist) && !is_chunk;
     float acc[NE];
 #pragma unroll
     for (int k = 0; k < NE; k++) acc[k] = start_at_xi ? xi[k] : 0.f;
 
     if (MODEL == kWalk)
-        gather_pairs<L, MODEL, true>(acc, xi, p.walks + (size_t)v * kWalkLen, kWalkLen, v, p, sd, lane);
+        gather_pairs<L, MODEL, true>(acc, xi, p.walks + (size_t)v * kWalkLen, active ? kWalkLen : 0, v, p, sd, l);
     else
-        gather_pairs<L, MODEL, true>(acc, xi, p.colids + it.e0, len, v, p, sd, lane);
+        gather_pairs<L, MODEL, true>(acc, xi, p.colids + it.e0, len, v, p, sd, l);
 
-    if (is_chunk) {
-        // split row: publish this chunk's partial sum; the last chunk to arrive folds them in
-        // chunk order (deterministic) and finishes the row.
-        sum_subgroups<L>(acc);
-        if (sub == 0) L::store_g(p.partials + (size_t)h.slot * rs, acc, l, p.dim);
+    // split rows: publish this chunk's partial sum; the last chunk to arrive folds all of them in
+    // chunk order (deterministic) and finishes the row.
+    bool finish = active;
+    if (__any_sync(kFull, is_chunk)) {
+        const uint32_t slot0 = h.slot - h.chunk;
+        if (is_chunk) L::store_g(p.partials + (size_t)h.slot * rs, acc, l, p.dim);
         __threadfence();
         __syncwarp();
         uint32_t old = 0;
-        const uint32_t slot0 = h.slot - h.chunk;
-        if (lane == 0) old = atomicAdd(p.counters + slot0, 1u);
-        old = __shfl_sync(kFull, old, 0);
-        if (old != h.nchunks - 1) return;
-        __threadfence();
-        if (lane == 0) p.counters[slot0] = 0;   // every chunk has arrived: re-arm for the next minibatch
+        if (is_chunk && l == 0) old = atomicAdd(p.counters + slot0, 1u);
+        old = __shfl_sync(kFull, old, 0, LPR);
+        const bool last = is_chunk && old == h.nchunks - 1;
+        if (is_chunk) finish = last;
+        if (last) {
+            __threadfence();
+            if (l == 0) p.counters[slot0] = 0;   // every chunk has arrived: re-arm for the next minibatch
 #pragma unroll
-        for (int k = 0; k < NE; k++) acc[k] = 0.f;
-        if (sub == 0) {
-            for (uint32_t c = 0; c < h.nchunks; c++) {
+            for (int k = 0; k < NE; k++) acc[k] = 0.f;
+            constexpr int CU = 4;                // partial rows in flight while folding
+            uint32_t c = 0;
+            for (; c + CU <= h.nchunks; c += CU) {
+                float part[CU][NE];
+#pragma unroll
+                for (int u = 0; u < CU; u++) L::load_g(part[u], p.partials + (size_t)(slot0 + c + u) * rs, l, p.dim);
+#pragma unroll
+                for (int u = 0; u < CU; u++)
+#pragma unroll
+                    for (int k = 0; k < NE; k++) acc[k] += part[u][k];
+            }
+            for (; c < h.nchunks; c++) {
                 float part[NE];
                 L::load_g(part, p.partials + (size_t)(slot0 + c) * rs, l, p.dim);
 #pragma unroll
@@ -323,23 +346,16 @@ __device__ __forceinline__ void process_item(const BatchParams& p, uint32_t t, c
     // repulsive part: s negatives (algorithms.cpp:614-627, 898-911, 1172-1183)
     if (s_neg != nullptr) {
         mbar_wait(neg_bar, neg_parity);
-        for (uint32_t q0 = 0; q0 < p.s; q0 += L::RPW) {
-            const uint32_t q = q0 + sub;
-            const bool valid = q < p.s;
+        for (uint32_t q = 0; q < p.s; q++) {
             float row[NE];
-            if (valid) L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
-            else {
-#pragma unroll
-                for (int k = 0; k < NE; k++) row[k] = xi[k];
-            }
-            pair_update<L, MODEL, false>(acc, xi, row, valid, p.lr, sd, p.lut);
+            L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
+            pair_update<L, MODEL, false>(acc, xi, row, finish, p.lr, sd, p.lut);
         }
     } else {
-        const uint32_t* nidx = p.neg + (p.bs_mode ? (size_t)((uint64_t)v - p.lo) : 0);
-        gather_pairs<L, MODEL, false>(acc, xi, nidx, p.s, v, p, sd, lane);
+        const uint32_t* nidx = p.neg + ((p.bs_mode && active) ? (size_t)((uint64_t)v - p.lo) : 0);
+        gather_pairs<L, MODEL, false>(acc, xi, nidx, finish ? p.s : 0u, v, p, sd, l);
     }
-    sum_subgroups<L>(acc);
-    if (sub == 0) {
+    if (finish) {
         if (MODEL == kTDist || is_chunk) {
 #pragma unroll
             for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(xi[k], acc[k]);   // X[i] += delta (:629-639)
@@ -366,8 +382,9 @@ __device__ __forceinline__ void stage_negatives(const BatchParams& p, float* s_n
 }
 
 // ------------------------------------------------------------------ kernels ------------
-// One launch per minibatch; one warp per item; the hardware CTA scheduler balances the load
-// (items are ordered hub chunks first, then rows by descending degree class).
+// One launch per minibatch; one group of lanes per item; the hardware CTA scheduler balances
+// the load (items are ordered hub chunks first, then rows by descending degree class, so the
+// groups of a warp get items of similar length).
 template <class L, int MODEL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 force_batch_kernel(const BatchParams p) {
@@ -381,8 +398,8 @@ force_batch_kernel(const BatchParams p) {
         stage_negatives<L>(p, s_neg, bar);
     }
     const int lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (t < p.n_items) process_item<L, MODEL>(p, t, s_neg, bar, 0, lane);
+    const uint32_t t_base = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * L::G;
+    if (t_base < p.n_items) process_items<L, MODEL>(p, t_base, s_neg, bar, 0, lane);
     // the CTA's shared memory must stay allocated until the bulk copies have landed
     if (s_neg != nullptr) mbar_wait(bar, 0);
 }

@@ -109,6 +109,9 @@ class Engine:
     def set_epoch_mode(self, mode):
         check(lib().f2v_set_epoch_mode(self._h, mode), "f2v_set_epoch_mode")
 
+    def set_option(self, name, value):
+        check(lib().f2v_set_option(self._h, name.encode(), int(value)), "f2v_set_option")
+
     def launch_count(self):
         return int(lib().f2v_launch_count(self._h))
 
