@@ -1,0 +1,64 @@
+"""Worker for tests/test_multi_gpu.py (one rank per GPU under torch.distributed.run)."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import force2vec_b200 as F  # noqa: E402
+from force2vec_b200 import host  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rp, ci = host.rmat_csr(13, 16, 2)
+    n = len(rp) - 1
+    ok = True
+    for model, bs, dim, batch in ((5, 0, 128, 512), (5, 1, 128, 512), (6, 0, 128, 1000), (7, 0, 64, 512), (6, 1, 64, 256)):
+        if batch % world:
+            batch += world - batch % world
+        g = host.RandStream(1)
+        X0 = g.init_embeddings(model, n, dim)
+        streams = []
+        for it in range(2):
+            w = g.walks(rp, ci).copy() if model == 7 else None
+            streams.append((w, g.epoch_negatives(model, n, batch, 5, bs).copy()))
+
+        def run(eng):
+            eng.set_embeddings(X0)
+            if model != 5:
+                eng.set_lut()
+            for w, neg in streams:
+                if w is not None:
+                    eng.set_walks(w)
+                eng.set_negatives(neg)
+                eng.run_epoch(model, batch, 5, bs, 0.02)
+            return eng.get_embeddings()
+
+        multi = F.Engine(rp, ci, dim, device=local)
+        ids = [F.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        multi.comm_init(ids[0], rank, world)
+        a = run(multi)
+        multi.close()
+        single = F.Engine(rp, ci, dim, device=local)
+        b = run(single)
+        single.close()
+        same = np.array_equal(a, b)
+        if not same:
+            print("rank", rank, "model", model, "bs", bs, "max diff", np.abs(a - b).max(), flush=True)
+        ok &= same
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_OK" if int(t.item()) == 1 else "MGPU_FAIL", flush=True)
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- each rank plans only
+its contiguous slice of every minibatch (f2v_plan_build with rank/world, the same code the
+engine uploads), computes that slice, and the slices are all-gathered before the next
+minibatch.  The per-slice compute is stood in for by the oracle so the test runs without a GPU;
+the result must equal the single-rank epoch bit for bit."""
+import os
+import sys
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, model, bs, batch, ret):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from force2vec_b200 import host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rp, ci = host.rmat_csr(9, 8, 3)
+    n = len(rp) - 1
+    dim, s, lr = 16, 5, 0.02
+    g = host.RandStream(1)                                     # every rank regenerates the same stream
+    X = g.init_embeddings(model, n, dim)
+    walks = g.walks(rp, ci) if model == 7 else None
+    W = (batch + s - 1) if (bs and model != 7) else s
+    neg = g.epoch_negatives(model, n, batch, s, bs).reshape(-1, W)
+    plan = host.plan_build(rp, batch, 8, walk=(model == 7), rank=rank, world=world)
+    nb = plan["nb"]
+    slice_rows = batch // world
+    pad = np.zeros((nb * batch, dim), np.float32)              # tables padded to whole minibatches
+    pad[:n] = X
+    for b in range(nb):
+        items = plan["items"][int(plan["item_ptr"][b]):int(plan["item_ptr"][b + 1])]
+        rows = np.unique(items["v"])
+        lo, hi = b * batch, min(n, (b + 1) * batch)
+        mine_lo = min(lo + rank * slice_rows, hi)
+        mine_hi = min(mine_lo + slice_rows, hi)
+        assert rows.tolist() == list(range(mine_lo, mine_hi))  # the plan is exactly the rank's slice
+        full_idx = np.zeros(max(s * batch, 1) + s, np.uint32)
+        full_idx[:W] = neg[b]
+        Xb = pad[:n].copy()
+        # vertex k of the minibatch uses idx[k..k+s-1]: shift the window to the slice origin
+        off = (mine_lo - lo) if (bs and model != 7) else 0
+        if mine_hi > mine_lo:
+            O.step(model, bs, rp, ci, Xb, mine_lo, mine_hi, full_idx[off:], s, lr, walks=walks)
+        send = torch.from_numpy(np.ascontiguousarray(
+            np.vstack([Xb[mine_lo:mine_hi], np.zeros((slice_rows - (mine_hi - mine_lo), dim), np.float32)])))
+        out = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(out, send)
+        pad[lo:lo + batch] = torch.cat(out).numpy()
+        pad[n:] = 0
+    if rank == 0:
+        ret["X"] = pad[:n].copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model,bs", [(5, 0), (5, 1), (6, 0), (7, 0)])
+def test_two_ranks_equal_one_rank(model, bs):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from force2vec_b200 import host
+    world, batch = 2, 96
+    port = 29500 + (os.getpid() + model * 7 + bs) % 2000
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, model, bs, batch, ret), nprocs=world, join=True)
+    rp, ci = host.rmat_csr(9, 8, 3)
+    want = O.run(model, bs, rp, ci, 16, 1, batch, 5, 0.02)["X"]
+    assert np.array_equal(ret["X"], want)
