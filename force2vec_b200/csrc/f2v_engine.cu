@@ -208,10 +208,14 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
     case 64: return launch_batch_m<VecL<64, 8, 4>>(model, p, st);
     case 128:
         switch (p.variant) {
-        case 1: return launch_batch_m<VecL<128, 32, 8>>(model, p, st);
-        case 2: return launch_batch_m<VecL<128, 8, 2>>(model, p, st);
-        case 3: return launch_batch_m<VecL<128, 16, 8>>(model, p, st);
-        default: return launch_batch_m<VecL<128, 16, 4>>(model, p, st);
+        case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st);
+        case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st);
+        case 3: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st);
+        case 4: return launch_batch_m<VecL<128, 8, 2, 3>>(model, p, st);
+        case 5: return launch_batch_m<VecL<128, 8, 1, 3>>(model, p, st);
+        case 6: return launch_batch_m<VecL<128, 16, 4, 2>>(model, p, st);
+        case 7: return launch_batch_m<VecL<128, 8, 1, 4>>(model, p, st);
+        default: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st);
         }
     case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st);
     default: break;

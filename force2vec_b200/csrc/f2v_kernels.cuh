@@ -94,8 +94,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // bytes of the row: a d=128 row is one 512-B transaction with LPR=32, two 256-B ones with
 // LPR=16).  Smaller LPR = more vertices in flight per warp (latency tolerance on short rows)
 // and fewer redundant per-pair scalar instructions.
-template <int D, int LPR_, int U_>
+template <int D, int LPR_, int U_, int MINB_ = 1>
 struct VecL {
+    static constexpr int MINB = MINB_;
     static constexpr int V4 = D / 4;
     static constexpr int LPR = LPR_;
     static constexpr int G = 32 / LPR;
@@ -131,6 +132,7 @@ struct VecL {
 // loads, still coalesced).
 template <int NV>
 struct GenL {
+    static constexpr int MINB = 1;
     static constexpr int LPR = 32;
     static constexpr int G = 1;
     static constexpr int NE = NV;
@@ -166,12 +168,16 @@ struct GenL {
 __device__ __forceinline__ float clamp5(float v) { return fminf(fmaxf(v, -5.0f), 5.0f); }
 
 // fast_SM(), algorithms.cpp:766-770; sum and product in double, truncation, no interpolation.
+// Branch-free: the index is taken from v clamped to [-6, 6] (entry 2048 exists and is 1.0f),
+// then the reference's two range tests select 1 / 0.
 __device__ __forceinline__ float fast_sm(const float* __restrict__ lut, float v) {
-    if (v > 6.0f) return 1.0f;
-    if (v < -6.0f) return 0.0f;
     const double res = (double)(float)(kLutSize / 12.0);   // SM_RESOLUTION, algorithms.h:49
-    int i = (int)(((double)v + 6.0) * res);
-    return __ldg(lut + i);
+    const float vc = fminf(fmaxf(v, -6.0f), 6.0f);
+    const int i = (int)(((double)vc + 6.0) * res);
+    float sg = __ldg(lut + i);
+    sg = v > 6.0f ? 1.0f : sg;
+    sg = v < -6.0f ? 0.0f : sg;
+    return sg;
 }
 
 template <int LPR>
@@ -211,8 +217,9 @@ __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&x
         dot = group_sum<L::LPR>(dot);
         float sg = fast_sm(lut, dot);
         if (ATTR) {
-            // algorithms.cpp:866  prev += STEP*degi*(1.0-d1)*x_j   (double intermediate)
-            float c = (float)((double)sd * (1.0 - (double)sg));
+            // algorithms.cpp:866  prev += STEP*degi*(1.0-d1)*x_j  with (STEP*degi)*(1.0-d1) formed in
+            // double and rounded once; fma(-sd, sg, sd) = sd*(1-sg) rounded once is the same value
+            float c = fmaf(-sd, sg, sd);
             c = valid ? c : 0.f;
 #pragma unroll
             for (int k = 0; k < L::NE; k++) acc[k] = fmaf(c, xp[k], acc[k]);
@@ -236,6 +243,9 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
                                              uint32_t self, const BatchParams& p, float sd, int l) {
     constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
+    const float* const Xlo = p.Xlo;
+    const float* const Xhi = p.Xhi;
+    const uint64_t split = p.split;
     const uint32_t cnt_max = L::G > 1 ? warp_max(cnt) : cnt;
     for (uint32_t base = 0; base < cnt_max; base += LPR) {
         const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
@@ -246,16 +256,13 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
             bool valid[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
+                // lanes past nb hold `self`, so an out-of-range slot re-reads the item's own row
+                // (an L1/L2 hit) instead of branching; its pair is zeroed through `valid`
                 const uint32_t slot = t0 + u;
                 const uint32_t j = __shfl_sync(kFull, mine, slot, LPR);
                 valid[u] = slot < nb;
-                if (valid[u]) {
-                    const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
-                    L::load_g(rows[u], src, l, p.dim);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < L::NE; k++) rows[u][k] = xi[k];
-                }
+                const float* src = ((uint64_t)j < split ? Xlo : Xhi) + (size_t)j * rs;
+                L::load_g(rows[u], src, l, p.dim);
             }
 #pragma unroll
             for (int u = 0; u < U; u++)
@@ -386,7 +393,7 @@ __device__ __forceinline__ void stage_negatives(const BatchParams& p, float* s_n
 // the load (items are ordered hub chunks first, then rows by descending degree class, so the
 // groups of a warp get items of similar length).
 template <class L, int MODEL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, L::MINB)
 force_batch_kernel(const BatchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
