@@ -95,7 +95,7 @@ def lib():
     L.f2v_write_embd.argtypes = [C.c_char_p, vp, u64, u32]
     L.f2v_write_mtx.argtypes = [C.c_char_p, u64, vp, vp]
     L.f2v_rmat_csr.argtypes = [i32, i32, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
-    L.f2v_plan_build.argtypes = [vp, u64, u64, u32, u32, i32, i32, i32, C.POINTER(u64), C.POINTER(vp),
+    L.f2v_plan_build.argtypes = [vp, u64, u64, u32, u32, u32, i32, i32, i32, C.POINTER(u64), C.POINTER(vp),
                                  C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.f2v_train.argtypes = [C.POINTER(TrainArgs), vp, C.POINTER(C.c_double)]
     _lib = L

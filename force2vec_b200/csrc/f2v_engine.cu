@@ -72,7 +72,7 @@ constexpr int kNcclFloat32 = 7;   // ncclFloat32 in nccl.h's ncclDataType_t
 
 // ------------------------------------------------------------------ engine -------------
 struct Plan {
-    uint32_t batch = 0, chunk = 0;
+    uint32_t batch = 0, chunk = 0, par = 0;
     bool walk = false;
     int rank = 0, world = 1;
     uint64_t first_row = 0, nrows = 0;      // row range covered (whole table for epochs)
@@ -113,6 +113,7 @@ struct f2v_engine {
     int epoch_mode = 0;
     int variant = 0;
     int neg_smem = 1;
+    int par = 0;                             // adaptive-chunk parallelism target (0 = fixed chunk)
     uint64_t launches = 0;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -132,12 +133,12 @@ static int ensure(void** p, uint64_t* cap, uint64_t need_bytes) {
 // Upload the host plan (f2v_plan.hpp) for rows [first_row, first_row+nrows) and size the
 // hub-row partial buffers.  Cached on (batch, chunk, walk, rank, world, range).
 static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrows, uint32_t batch,
-                      uint32_t chunk, bool walk, int rank, int world) {
-    if (pl.d_items && pl.batch == batch && pl.chunk == chunk && pl.walk == walk && pl.rank == rank &&
+                      uint32_t chunk, uint32_t par, bool walk, int rank, int world) {
+    if (pl.d_items && pl.batch == batch && pl.chunk == chunk && pl.par == par && pl.walk == walk && pl.rank == rank &&
         pl.world == world && pl.first_row == first_row && pl.nrows == nrows)
         return F2V_OK;
     HostPlan hp;
-    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, walk, rank, world, hp);
+    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, par, walk, rank, world, hp);
     const uint64_t nb = hp.nb, total = hp.items.size();
     std::vector<Item>& items = hp.items;
     std::vector<HubInfo>& hub = hp.hub;
@@ -168,7 +169,7 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         CU(cudaMemset(e->d_counters, 0, sizeof(uint32_t) * slots));
         e->slots_cap = slots;
     }
-    pl.batch = batch; pl.chunk = chunk; pl.walk = walk; pl.rank = rank; pl.world = world;
+    pl.batch = batch; pl.chunk = chunk; pl.par = par; pl.walk = walk; pl.rank = rank; pl.world = world;
     pl.first_row = first_row; pl.nrows = nrows; pl.nb = nb;
     pl.item_ptr.swap(item_ptr);
     pl.n_hub.swap(n_hub);
@@ -459,7 +460,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     if (s > 0 && !neg_idx) return fail(F2V_ERR_ARG, "neg_idx is null");
     r = f2v_set_negatives(e, neg_idx, neg_stride(model, nrows, s, bs_mode));
     if (r) return r;
-    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 64, model == F2V_WALK, 0, 1);
+    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 64, 0, model == F2V_WALK, 0, 1);
     if (r) return r;
     uint64_t cap_bytes = e->stage_cap;
     r = ensure((void**)&e->d_stage, &cap_bytes, sizeof(float) * (uint64_t)nrows * e->dim);
@@ -515,7 +516,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
         CU(cudaMalloc((void**)&e->d_X[1 - e->cur], sizeof(float) * e->rows_alloc * e->dim));
         CU(cudaMemsetAsync(e->d_X[1 - e->cur], 0, sizeof(float) * e->rows_alloc * e->dim, e->stream));
     }
-    r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, model == F2V_WALK, e->rank, e->world);
+    r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world);
     if (r) return r;
     const Plan& pl = e->epoch_plan;
     float* Xold = e->d_X[e->cur];
@@ -582,6 +583,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     if (!e || !name) return fail(F2V_ERR_ARG, "null argument");
     if (!strcmp(name, "variant")) e->variant = (int)value;
     else if (!strcmp(name, "neg_smem")) e->neg_smem = value != 0;
+    else if (!strcmp(name, "par")) e->par = (int)value;
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }

@@ -160,14 +160,18 @@ def test_mtx_roundtrip(tmp_path, oracle):
     assert np.array_equal(b[0], rp) and np.array_equal(b[1], ci)
 
 
-def _check_plan(rp, batch, chunk, world):
+def _hub_slots(nc):
+    return nc + ((nc + 31) // 32 if nc > 32 else 0)
+
+
+def _check_plan(rp, batch, chunk, world, par=0):
     n = len(rp) - 1
     deg = np.diff(rp.astype(np.int64))
     nb = (n + batch - 1) // batch
     seen_rows = np.zeros(n, np.int64)
     seen_edges = np.zeros(n, np.int64)
     for rank in range(world):
-        pl = host.plan_build(rp, batch, chunk, rank=rank, world=world)
+        pl = host.plan_build(rp, batch, chunk, rank=rank, world=world, par=par)
         assert pl["nb"] == nb
         it, hb = pl["items"], pl["hub"]
         for b in range(nb):
@@ -192,6 +196,7 @@ def _check_plan(rp, batch, chunk, world):
             # hub rows: chunks 0..nchunks-1 in order, contiguous edge ranges, distinct slots
             if nh:
                 hv = items["v"][:nh]
+                ranges = []
                 for v in np.unique(hv):
                     m = hv == v
                     h = hubs[:nh][m]
@@ -200,16 +205,34 @@ def _check_plan(rp, batch, chunk, world):
                     e0 = items["e0"][:nh][m].astype(np.int64)
                     assert e0[0] == rp[v] and np.array_equal(e0[1:], e0[:-1] + ln[:nh][m][:-1])
                     seen_rows[v] += 1
-                assert len(np.unique(hubs["slot"][:nh])) == nh
-                assert hubs["slot"][:nh].max() < nh
+                    # partial-sum slots: chunk c at slot0 + c; rows with > 32 chunks own extra
+                    # slots for the per-block sums; slot ranges of different rows are disjoint
+                    slot0 = int(h["slot"][0])
+                    assert h["slot"].tolist() == list(range(slot0, slot0 + len(h)))
+                    ranges.append((slot0, slot0 + _hub_slots(len(h))))
+                ranges.sort()
+                assert ranges[0][0] == 0 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
     assert (seen_rows == 1).all()
     assert np.array_equal(seen_edges, deg)
 
 
-@pytest.mark.parametrize("batch,chunk,world", [(256, 64, 1), (100, 8, 1), (5000, 16, 1), (256, 64, 2), (96, 8, 4)])
-def test_plan_covers_every_row_once(batch, chunk, world):
+@pytest.mark.parametrize("batch,chunk,world,par", [(256, 64, 1, 0), (100, 8, 1, 0), (5000, 16, 1, 0), (256, 64, 2, 0),
+                                                    (96, 8, 4, 0), (2048, 4, 1, 0), (512, 64, 1, 100), (2048, 64, 2, 4000)])
+def test_plan_covers_every_row_once(batch, chunk, world, par):
     rp, ci = host.rmat_csr(11, 16, 1)
-    _check_plan(rp, batch, chunk, world)
+    _check_plan(rp, batch, chunk, world, par)
+
+
+def test_plan_adaptive_chunk():
+    """par > 0: a minibatch with few edges is cut finer (down to 8), one with many keeps `chunk`."""
+    rp, ci = host.rmat_csr(12, 16, 1)
+    pl = host.plan_build(rp, 512, 64, par=256)
+    for b in range(pl["nb"]):
+        lo, hi = int(pl["item_ptr"][b]), int(pl["item_ptr"][b + 1])
+        ln = (pl["items"]["len"][lo:hi] & 0x7fffffff).astype(np.int64)
+        edges = int(rp[min(len(rp) - 1, (b + 1) * 512)] - rp[b * 512])
+        want = min(64, max(8, -(-edges // 256)))
+        assert ln.max() <= want
 
 
 def test_cli_without_gpu_exits_nonzero():
