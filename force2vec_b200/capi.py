@@ -35,7 +35,8 @@ class TrainArgs(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "lib", "libf2v.so")
+    # F2V_LIB lets development tools A/B two builds of the library in one GPU session
+    return os.environ.get("F2V_LIB") or os.path.join(HERE, "lib", "libf2v.so")
 
 
 _lib = None

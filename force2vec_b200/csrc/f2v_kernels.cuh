@@ -271,31 +271,6 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     }
 }
 
-// acc = rows[0] + rows[1] + ... + rows[cnt-1] (in that order), CU partial rows in flight.
-template <class L>
-__device__ __forceinline__ void fold_rows(float (&acc)[L::NE], const float* rows, uint32_t cnt, size_t rs,
-                                          int l, uint32_t dim) {
-    constexpr int NE = L::NE, CU = 4;
-#pragma unroll
-    for (int k = 0; k < NE; k++) acc[k] = 0.f;
-    uint32_t c = 0;
-    for (; c + CU <= cnt; c += CU) {
-        float part[CU][NE];
-#pragma unroll
-        for (int u = 0; u < CU; u++) L::load_g(part[u], rows + (size_t)(c + u) * rs, l, dim);
-#pragma unroll
-        for (int u = 0; u < CU; u++)
-#pragma unroll
-            for (int k = 0; k < NE; k++) acc[k] += part[u][k];
-    }
-    for (; c < cnt; c++) {
-        float part[NE];
-        L::load_g(part, rows + (size_t)c * rs, l, dim);
-#pragma unroll
-        for (int k = 0; k < NE; k++) acc[k] += part[k];
-    }
-}
-
 // G work items, one per group: items t_base .. t_base+G-1 (groups past n_items idle).
 // s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
 template <class L, int MODEL>
@@ -337,45 +312,42 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
     else
         gather_pairs<L, MODEL, true>(acc, xi, p.colids + it.e0, len, v, p, sd, l);
 
-    // split rows: publish this chunk's partial sum; the last chunk of a fold block to arrive folds
-    // the block in chunk order, and (rows with more than kFoldBlock chunks) the last block to
-    // arrive folds the block sums in block order: deterministic, no float atomics, and a
-    // critical path of ~2*kFoldBlock partial rows for the largest hubs.
+    // split rows: publish this chunk's partial sum; the last chunk to arrive folds all of them in
+    // chunk order (deterministic) and finishes the row.
     bool finish = active;
     if (__any_sync(kFull, is_chunk)) {
         const uint32_t slot0 = h.slot - h.chunk;
-        const uint32_t nblk = (h.nchunks + kFoldBlock - 1) / kFoldBlock;
-        const uint32_t blk = h.chunk / kFoldBlock;
-        const uint32_t blk_n = min(kFoldBlock, h.nchunks - blk * kFoldBlock);
         if (is_chunk) L::store_g(p.partials + (size_t)h.slot * rs, acc, l, p.dim);
         __threadfence();
         __syncwarp();
         uint32_t old = 0;
-        if (is_chunk && l == 0) old = atomicAdd(p.counters + slot0 + blk, 1u);
+        if (is_chunk && l == 0) old = atomicAdd(p.counters + slot0, 1u);
         old = __shfl_sync(kFull, old, 0, LPR);
-        bool last = is_chunk && old == blk_n - 1;
+        const bool last = is_chunk && old == h.nchunks - 1;
+        if (is_chunk) finish = last;
         if (last) {
             __threadfence();
-            if (l == 0) p.counters[slot0 + blk] = 0;     // re-arm for the next minibatch
-            fold_rows<L>(acc, p.partials + (size_t)(slot0 + blk * kFoldBlock) * rs, blk_n, rs, l, p.dim);
-        }
-        const bool second = last && nblk > 1;
-        if (__any_sync(kFull, second)) {
-            if (second) L::store_g(p.partials + (size_t)(slot0 + h.nchunks + blk) * rs, acc, l, p.dim);
-            __threadfence();
-            __syncwarp();
-            old = 0;
-            if (second && l == 0) old = atomicAdd(p.counters + slot0 + nblk, 1u);
-            old = __shfl_sync(kFull, old, 0, LPR);
-            const bool last2 = second && old == nblk - 1;
-            if (last2) {
-                __threadfence();
-                if (l == 0) p.counters[slot0 + nblk] = 0;
-                fold_rows<L>(acc, p.partials + (size_t)(slot0 + h.nchunks) * rs, nblk, rs, l, p.dim);
+            if (l == 0) p.counters[slot0] = 0;   // every chunk has arrived: re-arm for the next minibatch
+#pragma unroll
+            for (int k = 0; k < NE; k++) acc[k] = 0.f;
+            constexpr int CU = 4;                // partial rows in flight while folding
+            uint32_t c = 0;
+            for (; c + CU <= h.nchunks; c += CU) {
+                float part[CU][NE];
+#pragma unroll
+                for (int u = 0; u < CU; u++) L::load_g(part[u], p.partials + (size_t)(slot0 + c + u) * rs, l, p.dim);
+#pragma unroll
+                for (int u = 0; u < CU; u++)
+#pragma unroll
+                    for (int k = 0; k < NE; k++) acc[k] += part[u][k];
             }
-            if (second) last = last2;
+            for (; c < h.nchunks; c++) {
+                float part[NE];
+                L::load_g(part, p.partials + (size_t)(slot0 + c) * rs, l, p.dim);
+#pragma unroll
+                for (int k = 0; k < NE; k++) acc[k] += part[k];
+            }
         }
-        if (is_chunk) finish = last;
     }
 
     // repulsive part: s negatives (algorithms.cpp:614-627, 898-911, 1172-1183)

@@ -21,14 +21,10 @@ struct alignas(16) HubInfo {
     uint32_t deg;     // full degree of the row
 };
 
-constexpr uint32_t kFoldBlock = 32;   // hub partial sums are folded in blocks of 32, then across blocks
 constexpr uint32_t kMinChunk = 8;
 
-// partial-sum / counter slots a split row needs: one per chunk, plus one per fold block when
-// the row has more than kFoldBlock chunks (two-level fold)
-inline uint32_t hub_slots(uint64_t nchunks) {
-    return (uint32_t)(nchunks + (nchunks > kFoldBlock ? (nchunks + kFoldBlock - 1) / kFoldBlock : 0));
-}
+// partial-sum / counter slots a split row needs: one per chunk (the counter is the first one)
+inline uint32_t hub_slots(uint64_t nchunks) { return (uint32_t)nchunks; }
 
 struct HostPlan {
     uint64_t nb = 0;

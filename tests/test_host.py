@@ -161,7 +161,7 @@ def test_mtx_roundtrip(tmp_path, oracle):
 
 
 def _hub_slots(nc):
-    return nc + ((nc + 31) // 32 if nc > 32 else 0)
+    return nc
 
 
 def _check_plan(rp, batch, chunk, world, par=0):
@@ -205,8 +205,7 @@ def _check_plan(rp, batch, chunk, world, par=0):
                     e0 = items["e0"][:nh][m].astype(np.int64)
                     assert e0[0] == rp[v] and np.array_equal(e0[1:], e0[:-1] + ln[:nh][m][:-1])
                     seen_rows[v] += 1
-                    # partial-sum slots: chunk c at slot0 + c; rows with > 32 chunks own extra
-                    # slots for the per-block sums; slot ranges of different rows are disjoint
+                    # partial-sum slots: chunk c at slot0 + c; slot ranges of different rows are disjoint
                     slot0 = int(h["slot"][0])
                     assert h["slot"].tolist() == list(range(slot0, slot0 + len(h)))
                     ranges.append((slot0, slot0 + _hub_slots(len(h))))

@@ -50,7 +50,10 @@ def main():
         eng.set_negatives(neg)
         eng.set_option("variant", var)
         eng.set_option("neg_smem", ns)
-        eng.set_option("par", par)
+        try:
+            eng.set_option("par", par)
+        except F.F2VError:
+            pass
         try:
             eng.set_epoch_mode(mode)
         except F.F2VError as ex:
