@@ -111,9 +111,9 @@ struct f2v_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     int epoch_mode = 0;
-    int variant = 0;
+    int variant = 3;
     int neg_smem = 1;
-    int par = 0;                             // adaptive-chunk parallelism target (0 = fixed chunk)
+    int par = 9472;                          // adaptive-chunk target: 148 SMs x 64 lane groups (0 = fixed chunk)
     uint64_t launches = 0;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -211,12 +211,12 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         switch (p.variant) {
         case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st);
         case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st);
-        case 3: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st);
+        case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st);
         case 4: return launch_batch_m<VecL<128, 8, 2, 3>>(model, p, st);
         case 5: return launch_batch_m<VecL<128, 8, 1, 3>>(model, p, st);
         case 6: return launch_batch_m<VecL<128, 16, 4, 2>>(model, p, st);
         case 7: return launch_batch_m<VecL<128, 8, 1, 4>>(model, p, st);
-        default: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st);
+        default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st);   // 3
         }
     case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st);
     default: break;
@@ -493,7 +493,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
     if (batch == 0) return fail(F2V_ERR_ARG, "batch must be > 0");
     if (e->world > 1 && batch % e->world) return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
     CU(cudaSetDevice(e->device));
-    if (chunk == 0) chunk = 64;
+    if (chunk == 0) chunk = 128;
     const uint64_t nb = (e->n + batch - 1) / batch;
     const uint64_t W = neg_stride(model, batch, s, bs_mode);
     if (e->neg_count < e->neg_off + nb * W)
