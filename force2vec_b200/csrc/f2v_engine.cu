@@ -460,7 +460,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     if (s > 0 && !neg_idx) return fail(F2V_ERR_ARG, "neg_idx is null");
     r = f2v_set_negatives(e, neg_idx, neg_stride(model, nrows, s, bs_mode));
     if (r) return r;
-    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 64, 0, model == F2V_WALK, 0, 1);
+    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 128, (uint32_t)e->par, model == F2V_WALK, 0, 1);
     if (r) return r;
     uint64_t cap_bytes = e->stage_cap;
     r = ensure((void**)&e->d_stage, &cap_bytes, sizeof(float) * (uint64_t)nrows * e->dim);

@@ -126,6 +126,57 @@ struct VecL {
             __stcg(reinterpret_cast<float4*>(row) + k * LPR + l,
                    make_float4(f[4 * k + 0], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
     }
+    // ---- arithmetic on a lane's fragment: packed fp32x2 (FFMA2 / FMUL2 / FADD2 on sm_100a;
+    //      every component is rounded exactly like the scalar op)
+    __device__ static __forceinline__ float dot(const float (&a)[NE], const float (&b)[NE]) {
+        float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < NE; k += 2)
+            s = __ffma2_rn(make_float2(a[k], a[k + 1]), make_float2(b[k], b[k + 1]), s);
+        return s.x + s.y;
+    }
+    // acc += c * x   (single rounding per component)
+    __device__ static __forceinline__ void axpy(float (&acc)[NE], float c, const float (&x)[NE]) {
+        const float2 c2 = make_float2(c, c);
+#pragma unroll
+        for (int k = 0; k < NE; k += 2) {
+            float2 r = __ffma2_rn(c2, make_float2(x[k], x[k + 1]), make_float2(acc[k], acc[k + 1]));
+            acc[k] = r.x; acc[k + 1] = r.y;
+        }
+    }
+    // acc = acc - round(c * x)   (two roundings per component, as the reference's float expression)
+    __device__ static __forceinline__ void sub_mul(float (&acc)[NE], float c, const float (&x)[NE]) {
+        const float2 cn = make_float2(-c, -c);
+#pragma unroll
+        for (int k = 0; k < NE; k += 2) {
+            float2 r = __fadd2_rn(make_float2(acc[k], acc[k + 1]), __fmul2_rn(cn, make_float2(x[k], x[k + 1])));
+            acc[k] = r.x; acc[k + 1] = r.y;
+        }
+    }
+    // d = a - b, returns this lane's sum of d^2
+    __device__ static __forceinline__ float diff_ss(float (&d)[NE], const float (&a)[NE], const float (&b)[NE]) {
+        const float2 m1 = make_float2(-1.f, -1.f);
+        float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < NE; k += 2) {
+            float2 t = __ffma2_rn(make_float2(b[k], b[k + 1]), m1, make_float2(a[k], a[k + 1]));   // a - b, exact product
+            d[k] = t.x; d[k + 1] = t.y;
+            s = __ffma2_rn(t, t, s);
+        }
+        return s.x + s.y;
+    }
+    // acc = acc + round(w * clamp5(round(d * d1)))
+    __device__ static __forceinline__ void clamp_acc(float (&acc)[NE], const float (&d)[NE], float d1, float w) {
+        const float2 d2 = make_float2(d1, d1), w2 = make_float2(w, w);
+#pragma unroll
+        for (int k = 0; k < NE; k += 2) {
+            float2 t = __fmul2_rn(make_float2(d[k], d[k + 1]), d2);
+            t.x = fminf(fmaxf(t.x, -5.0f), 5.0f);
+            t.y = fminf(fmaxf(t.y, -5.0f), 5.0f);
+            float2 r = __fadd2_rn(make_float2(acc[k], acc[k + 1]), __fmul2_rn(w2, t));
+            acc[k] = r.x; acc[k + 1] = r.y;
+        }
+    }
 };
 
 // GenL<NV>: any dim <= 32*NV; one group per warp, lane l holds elements l, l+32, ... (scalar
@@ -160,6 +211,34 @@ struct GenL {
             if (e < dim) __stcg(row + e, f[k]);
         }
     }
+    __device__ static __forceinline__ float dot(const float (&a)[NE], const float (&b)[NE]) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NE; k++) s = fmaf(a[k], b[k], s);
+        return s;
+    }
+    __device__ static __forceinline__ void axpy(float (&acc)[NE], float c, const float (&x)[NE]) {
+#pragma unroll
+        for (int k = 0; k < NE; k++) acc[k] = fmaf(c, x[k], acc[k]);
+    }
+    __device__ static __forceinline__ void sub_mul(float (&acc)[NE], float c, const float (&x)[NE]) {
+#pragma unroll
+        for (int k = 0; k < NE; k++) acc[k] = __fsub_rn(acc[k], __fmul_rn(c, x[k]));
+    }
+    __device__ static __forceinline__ float diff_ss(float (&d)[NE], const float (&a)[NE], const float (&b)[NE]) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NE; k++) {
+            d[k] = __fsub_rn(a[k], b[k]);
+            s = fmaf(d[k], d[k], s);
+        }
+        return s;
+    }
+    __device__ static __forceinline__ void clamp_acc(float (&acc)[NE], const float (&d)[NE], float d1, float w) {
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+            acc[k] = __fadd_rn(acc[k], __fmul_rn(w, fminf(fmaxf(__fmul_rn(d[k], d1), -5.0f), 5.0f)));
+    }
 };
 
 // ------------------------------------------------------------------ scalar pieces ------
@@ -187,49 +266,63 @@ __device__ __forceinline__ float group_sum(float x) {
     return x;
 }
 
-// One (i, p) pair of one group.  ATTR: attractive (neighbour / walk sample) or repulsive
-// (negative).  Executed by the whole warp (the reduction shuffles are warp-wide); groups with
-// nothing to do pass valid = false and contribute exactly zero.
+// Per-pair scalar from the reduced squared distance / dot product `r`.
+//   option 5: the factor d1 (algorithms.cpp:608 d1 = -2.0/(1.0+attrc); :622 d1 = 2.0/(repuls*(1.0+repuls)))
+//   option 6/7: the coefficient of x_p: attractive STEP*degi*(1.0-sigma) formed in double and
+//   rounded once (:866) == fma(-sd, sg, sd); repulsive STEP*sigma in float (:908)
+template <int MODEL, bool ATTR>
+__device__ __forceinline__ float pair_scalar(float r, float lr, float sd, const float* __restrict__ lut) {
+    if (MODEL == kTDist)
+        return ATTR ? __fdiv_rn(-2.0f, __fadd_rn(1.0f, r)) : __fdiv_rn(2.0f, __fmul_rn(r, __fadd_rn(1.0f, r)));
+    const float sg = fast_sm(lut, r);
+    return ATTR ? fmaf(-sd, sg, sd) : __fmul_rn(lr, sg);
+}
+
+template <class L, int MODEL, bool ATTR>
+__device__ __forceinline__ void pair_apply(float (&acc)[L::NE], const float (&xp)[L::NE], const float (&d)[L::NE],
+                                           float sc, bool valid, float lr) {
+    if (MODEL == kTDist) L::clamp_acc(acc, d, sc, valid ? lr : 0.f);      // prev += STEP*scale(diff*d1)
+    else if (ATTR) L::axpy(acc, valid ? sc : 0.f, xp);                     // prev += c*x_j
+    else L::sub_mul(acc, valid ? sc : 0.f, xp);                            // prev -= (STEP*d1)*sample
+}
+
+// One (i, p) pair per group.  ATTR: attractive (neighbour / walk sample) or repulsive (negative).
+// Executed by the whole warp (the reduction shuffles are warp-wide); groups with nothing to do
+// pass valid = false and contribute exactly zero.
 template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&xi)[L::NE],
                                             const float (&xp)[L::NE], bool valid, float lr, float sd,
                                             const float* __restrict__ lut) {
-    if (MODEL == kTDist) {
-        float d[L::NE];
-        float ss = 0.f;
+    float d[L::NE];
+    float r = MODEL == kTDist ? L::diff_ss(d, xi, xp) : L::dot(xi, xp);
+    r = group_sum<L::LPR>(r);
+    const float sc = pair_scalar<MODEL, ATTR>(r, lr, sd, lut);
+    pair_apply<L, MODEL, ATTR>(acc, xp, d, sc, valid, lr);
+}
+
+// Two pairs per group at once: the two lane-partial sums are reduced with a halving butterfly
+// (lower half of the group ends up with pair 0's total, upper half with pair 1's: log2(LPR)
+// shuffles for both instead of 2*log2(LPR)), each half evaluates the scalar of ITS pair once,
+// and one more shuffle swaps the results.  Updates are applied in pair order (0 then 1).
+template <class L, int MODEL, bool ATTR>
+__device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&xi)[L::NE],
+                                             const float (&x0)[L::NE], const float (&x1)[L::NE],
+                                             bool v0, bool v1, float lr, float sd,
+                                             const float* __restrict__ lut, int l) {
+    constexpr int H = L::LPR / 2;
+    float d0[L::NE], d1[L::NE];
+    const float p0 = MODEL == kTDist ? L::diff_ss(d0, xi, x0) : L::dot(xi, x0);
+    const float p1 = MODEL == kTDist ? L::diff_ss(d1, xi, x1) : L::dot(xi, x1);
+    const bool hi = (l & H) != 0;
+    float keep = hi ? p1 : p0;
+    keep += __shfl_xor_sync(kFull, hi ? p0 : p1, H);
 #pragma unroll
-        for (int k = 0; k < L::NE; k++) {
-            d[k] = __fsub_rn(xi[k], xp[k]);
-            ss = fmaf(d[k], d[k], ss);
-        }
-        ss = group_sum<L::LPR>(ss);
-        // algorithms.cpp:608 d1 = -2.0/(1.0+attrc);  :622 d1 = 2.0/(repuls*(1.0+repuls))
-        float d1 = ATTR ? __fdiv_rn(-2.0f, __fadd_rn(1.0f, ss))
-                        : __fdiv_rn(2.0f, __fmul_rn(ss, __fadd_rn(1.0f, ss)));
-        float w = valid ? lr : 0.f;
-#pragma unroll
-        for (int k = 0; k < L::NE; k++)
-            acc[k] = __fadd_rn(acc[k], __fmul_rn(w, clamp5(__fmul_rn(d[k], d1))));
-    } else {
-        float dot = 0.f;
-#pragma unroll
-        for (int k = 0; k < L::NE; k++) dot = fmaf(xi[k], xp[k], dot);
-        dot = group_sum<L::LPR>(dot);
-        float sg = fast_sm(lut, dot);
-        if (ATTR) {
-            // algorithms.cpp:866  prev += STEP*degi*(1.0-d1)*x_j  with (STEP*degi)*(1.0-d1) formed in
-            // double and rounded once; fma(-sd, sg, sd) = sd*(1-sg) rounded once is the same value
-            float c = fmaf(-sd, sg, sd);
-            c = valid ? c : 0.f;
-#pragma unroll
-            for (int k = 0; k < L::NE; k++) acc[k] = fmaf(c, xp[k], acc[k]);
-        } else {
-            // algorithms.cpp:908  prev -= STEP*d1*sample   (float)
-            float c = valid ? __fmul_rn(lr, sg) : 0.f;
-#pragma unroll
-            for (int k = 0; k < L::NE; k++) acc[k] = __fsub_rn(acc[k], __fmul_rn(c, xp[k]));
-        }
-    }
+    for (int off = H / 2; off >= 1; off >>= 1) keep += __shfl_xor_sync(kFull, keep, off);
+    const float mine = pair_scalar<MODEL, ATTR>(keep, lr, sd, lut);
+    const float other = __shfl_xor_sync(kFull, mine, H);
+    const float s0 = hi ? other : mine, s1 = hi ? mine : other;
+    pair_apply<L, MODEL, ATTR>(acc, x0, d0, s0, v0, lr);
+    pair_apply<L, MODEL, ATTR>(acc, x1, d1, s1, v1, lr);
 }
 
 __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(kFull, v); }
@@ -264,9 +357,16 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
                 const float* src = ((uint64_t)j < split ? Xlo : Xhi) + (size_t)j * rs;
                 L::load_g(rows[u], src, l, p.dim);
             }
+            if (U % 2 == 0) {
 #pragma unroll
-            for (int u = 0; u < U; u++)
-                pair_update<L, MODEL, ATTR>(acc, xi, rows[u], valid[u], p.lr, sd, p.lut);
+                for (int u = 0; u < U; u += 2)
+                    pair2_update<L, MODEL, ATTR>(acc, xi, rows[u], rows[u + 1 < U ? u + 1 : u], valid[u],
+                                                 valid[u + 1 < U ? u + 1 : u], p.lr, sd, p.lut, l);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    pair_update<L, MODEL, ATTR>(acc, xi, rows[u], valid[u], p.lr, sd, p.lut);
+            }
         }
     }
 }
@@ -353,7 +453,14 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
     // repulsive part: s negatives (algorithms.cpp:614-627, 898-911, 1172-1183)
     if (s_neg != nullptr) {
         mbar_wait(neg_bar, neg_parity);
-        for (uint32_t q = 0; q < p.s; q++) {
+        uint32_t q = 0;
+        for (; q + 2 <= p.s; q += 2) {
+            float r0[NE], r1[NE];
+            L::load_s(r0, s_neg + (size_t)q * rs, l, p.dim);
+            L::load_s(r1, s_neg + (size_t)(q + 1) * rs, l, p.dim);
+            pair2_update<L, MODEL, false>(acc, xi, r0, r1, finish, finish, p.lr, sd, p.lut, l);
+        }
+        if (q < p.s) {
             float row[NE];
             L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
             pair_update<L, MODEL, false>(acc, xi, row, finish, p.lr, sd, p.lut);
