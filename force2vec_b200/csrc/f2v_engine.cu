@@ -113,6 +113,8 @@ struct f2v_engine {
     int epoch_mode = 0;
     int variant = 3;
     int neg_smem = 1;
+    int prefetch = 0;
+    int persist = 0;                         // 1: persistent CTAs striding over the item list (measured slower)
     int par = 9472;                          // adaptive-chunk target: 148 SMs x 64 lane groups (0 = fixed chunk)
     uint64_t launches = 0;
     int rank = 0, world = 1;
@@ -178,55 +180,68 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
 }
 
 // ------------------------------------------------------------------ dispatch -----------
-template <class L, int MODEL>
-static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st) {
+template <class L, int MODEL, bool PERSIST>
+static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_count) {
     if (p.n_items == 0) return cudaSuccess;
+    auto kern = force_batch_kernel<L, MODEL, PERSIST>;
+    const bool negs = L::kBulk && p.neg_in_smem;
+    const bool lut_s = PERSIST && MODEL != kTDist && L::kBulk;
     size_t smem = 0;
-    if (L::kBulk && p.neg_in_smem) smem = 128 + (size_t)p.s * p.dim * sizeof(float);
+    if (negs || lut_s) smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0) + (lut_s ? kLutAlloc * sizeof(float) : 0);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(force_batch_kernel<L, MODEL>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned per_cta = kWarpsPerCta * L::G;
     unsigned grid = (p.n_items + per_cta - 1) / per_cta;
-    force_batch_kernel<L, MODEL><<<grid, kWarpsPerCta * 32, smem, st>>>(p);
+    if (PERSIST) {
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
+        if (e != cudaSuccess) return e;
+        grid = std::min<unsigned>(grid, (unsigned)(sm_count * std::max(per_sm, 1)));
+    }
+    kern<<<grid, kWarpsPerCta * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
+template <class L, int MODEL>
+static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
+    return persist ? launch_batch_k<L, MODEL, true>(p, st, sm_count) : launch_batch_k<L, MODEL, false>(p, st, sm_count);
+}
+
 template <class L>
-static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t st) {
+static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
     switch (model) {
-    case kTDist: return launch_batch_t<L, kTDist>(p, st);
-    case kSigmoid: return launch_batch_t<L, kSigmoid>(p, st);
-    default: return launch_batch_t<L, kWalk>(p, st);
+    case kTDist: return launch_batch_t<L, kTDist>(p, st, sm_count, persist);
+    case kSigmoid: return launch_batch_t<L, kSigmoid>(p, st, sm_count, persist);
+    default: return launch_batch_t<L, kWalk>(p, st, sm_count, persist);
     }
 }
 
-static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st) {
+static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
     switch (p.dim) {
-    case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st);
-    case 64: return launch_batch_m<VecL<64, 8, 4>>(model, p, st);
+    case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st, sm_count, persist);
+    case 64: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count, persist);
     case 128:
         switch (p.variant) {
-        case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st);
-        case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st);
-        case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st);
-        case 4: return launch_batch_m<VecL<128, 8, 2, 3>>(model, p, st);
-        case 5: return launch_batch_m<VecL<128, 8, 1, 3>>(model, p, st);
-        case 6: return launch_batch_m<VecL<128, 16, 4, 2>>(model, p, st);
-        case 7: return launch_batch_m<VecL<128, 8, 1, 4>>(model, p, st);
-        default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st);   // 3
+        case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st, sm_count, persist);
+        case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st, sm_count, persist);
+        case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count, persist);
+        case 4: return launch_batch_m<VecL<128, 8, 2, 3>>(model, p, st, sm_count, persist);
+        case 5: return launch_batch_m<VecL<128, 8, 1, 3>>(model, p, st, sm_count, persist);
+        case 6: return launch_batch_m<VecL<128, 16, 4, 2>>(model, p, st, sm_count, persist);
+        case 7: return launch_batch_m<VecL<128, 8, 1, 4>>(model, p, st, sm_count, persist);
+        default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st, sm_count, persist);   // 3
         }
-    case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st);
+    case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st, sm_count, persist);
     default: break;
     }
-    if (p.dim <= 32) return launch_batch_m<GenL<1>>(model, p, st);
-    if (p.dim <= 64) return launch_batch_m<GenL<2>>(model, p, st);
-    if (p.dim <= 128) return launch_batch_m<GenL<4>>(model, p, st);
-    if (p.dim <= 256) return launch_batch_m<GenL<8>>(model, p, st);
-    if (p.dim <= 512) return launch_batch_m<GenL<16>>(model, p, st);
-    return launch_batch_m<GenL<32>>(model, p, st);
+    if (p.dim <= 32) return launch_batch_m<GenL<1>>(model, p, st, sm_count, persist);
+    if (p.dim <= 64) return launch_batch_m<GenL<2>>(model, p, st, sm_count, persist);
+    if (p.dim <= 128) return launch_batch_m<GenL<4>>(model, p, st, sm_count, persist);
+    if (p.dim <= 256) return launch_batch_m<GenL<8>>(model, p, st, sm_count, persist);
+    if (p.dim <= 512) return launch_batch_m<GenL<16>>(model, p, st, sm_count, persist);
+    return launch_batch_m<GenL<32>>(model, p, st, sm_count, persist);
 }
 
 static bool bulk_ok(const f2v_engine* e, uint32_t s, int bs_mode) {
@@ -475,8 +490,8 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     p.colids = e->d_colids; p.neg = e->d_neg; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
-    p.lr = lr; p.variant = e->variant;
-    CU(launch_batch(model, p, e->stream));
+    p.lr = lr; p.variant = e->variant; p.prefetch = e->prefetch;
+    CU(launch_batch(model, p, e->stream, e->sm_count, e->persist));
     e->launches++;
     // apply after the join (algorithms.cpp:629-639 / :913-921)
     CU(cudaMemcpyAsync(e->d_X[e->cur] + first_row * e->dim, e->d_stage, sizeof(float) * (uint64_t)nrows * e->dim,
@@ -527,7 +542,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
     p.colids = e->d_colids; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
-    p.lr = lr; p.variant = e->variant;
+    p.lr = lr; p.variant = e->variant; p.prefetch = e->prefetch;
     const uint64_t slice = batch / (uint64_t)e->world;
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
@@ -538,7 +553,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
         p.split = b * batch;
         p.neg = e->d_neg + e->neg_off + b * W;
         if (p.n_items) {
-            CU(launch_batch(model, p, e->stream));
+            CU(launch_batch(model, p, e->stream, e->sm_count, e->persist));
             e->launches++;
         }
         if (e->world > 1) {
@@ -584,6 +599,8 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     if (!strcmp(name, "variant")) e->variant = (int)value;
     else if (!strcmp(name, "neg_smem")) e->neg_smem = value != 0;
     else if (!strcmp(name, "par")) e->par = (int)value;
+    else if (!strcmp(name, "prefetch")) e->prefetch = (int)value;
+    else if (!strcmp(name, "persist")) e->persist = value != 0;
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }

@@ -22,6 +22,13 @@
 #include <stdint.h>
 #include "f2v_plan.hpp"
 
+// How gathered embedding rows are loaded: __ldcg (L2 only), __ldca (L1 + L2) or __ldg
+// (non-coherent path).  Every row a launch gathers is read-only for that launch (it writes only
+// rows of its own minibatch into the next table, which it never reads), so all three are legal.
+#ifndef F2V_ROW_LOAD
+#define F2V_ROW_LOAD __ldcg
+#endif
+
 namespace f2v {
 
 constexpr int kTDist = 5, kSigmoid = 6, kWalk = 7;
@@ -53,6 +60,7 @@ struct BatchParams {
     int bs_mode;
     int neg_in_smem;
     int variant;          // layout variant of the d=128 kernels (tuning knob)
+    int prefetch;         // 0 none, 1 TMA bulk L2 prefetch of a whole index block's rows, 2 per-line L2 prefetch
     float lr;
 };
 
@@ -76,6 +84,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA bulk prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address into L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void line_prefetch_l2(const void* gmem) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -109,7 +124,7 @@ struct VecL {
     __device__ static __forceinline__ void load_g(float (&f)[NE], const float* row, int l, uint32_t) {
 #pragma unroll
         for (int k = 0; k < VPL; k++) {
-            float4 t = __ldcg(reinterpret_cast<const float4*>(row) + k * LPR + l);
+            float4 t = F2V_ROW_LOAD(reinterpret_cast<const float4*>(row) + k * LPR + l);
             f[4 * k + 0] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
         }
     }
@@ -249,11 +264,17 @@ __device__ __forceinline__ float clamp5(float v) { return fminf(fmaxf(v, -5.0f),
 // fast_SM(), algorithms.cpp:766-770; sum and product in double, truncation, no interpolation.
 // Branch-free: the index is taken from v clamped to [-6, 6] (entry 2048 exists and is 1.0f),
 // then the reference's two range tests select 1 / 0.
+template <bool LS>
 __device__ __forceinline__ float fast_sm(const float* __restrict__ lut, float v) {
     const double res = (double)(float)(kLutSize / 12.0);   // SM_RESOLUTION, algorithms.h:49
     const float vc = fminf(fmaxf(v, -6.0f), 6.0f);
     const int i = (int)(((double)vc + 6.0) * res);
-    float sg = __ldg(lut + i);
+    float sg;
+    if (LS) {   // table staged in shared memory (persistent CTAs)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sg) : "r"(smem_u32(lut) + 4u * (uint32_t)i));
+    } else {
+        sg = __ldg(lut + i);
+    }
     sg = v > 6.0f ? 1.0f : sg;
     sg = v < -6.0f ? 0.0f : sg;
     return sg;
@@ -270,11 +291,11 @@ __device__ __forceinline__ float group_sum(float x) {
 //   option 5: the factor d1 (algorithms.cpp:608 d1 = -2.0/(1.0+attrc); :622 d1 = 2.0/(repuls*(1.0+repuls)))
 //   option 6/7: the coefficient of x_p: attractive STEP*degi*(1.0-sigma) formed in double and
 //   rounded once (:866) == fma(-sd, sg, sd); repulsive STEP*sigma in float (:908)
-template <int MODEL, bool ATTR>
+template <int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ float pair_scalar(float r, float lr, float sd, const float* __restrict__ lut) {
     if (MODEL == kTDist)
         return ATTR ? __fdiv_rn(-2.0f, __fadd_rn(1.0f, r)) : __fdiv_rn(2.0f, __fmul_rn(r, __fadd_rn(1.0f, r)));
-    const float sg = fast_sm(lut, r);
+    const float sg = fast_sm<LS>(lut, r);
     return ATTR ? fmaf(-sd, sg, sd) : __fmul_rn(lr, sg);
 }
 
@@ -289,14 +310,14 @@ __device__ __forceinline__ void pair_apply(float (&acc)[L::NE], const float (&xp
 // One (i, p) pair per group.  ATTR: attractive (neighbour / walk sample) or repulsive (negative).
 // Executed by the whole warp (the reduction shuffles are warp-wide); groups with nothing to do
 // pass valid = false and contribute exactly zero.
-template <class L, int MODEL, bool ATTR>
+template <class L, int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&xi)[L::NE],
                                             const float (&xp)[L::NE], bool valid, float lr, float sd,
                                             const float* __restrict__ lut) {
     float d[L::NE];
     float r = MODEL == kTDist ? L::diff_ss(d, xi, xp) : L::dot(xi, xp);
     r = group_sum<L::LPR>(r);
-    const float sc = pair_scalar<MODEL, ATTR>(r, lr, sd, lut);
+    const float sc = pair_scalar<MODEL, ATTR, LS>(r, lr, sd, lut);
     pair_apply<L, MODEL, ATTR>(acc, xp, d, sc, valid, lr);
 }
 
@@ -304,7 +325,7 @@ __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&x
 // (lower half of the group ends up with pair 0's total, upper half with pair 1's: log2(LPR)
 // shuffles for both instead of 2*log2(LPR)), each half evaluates the scalar of ITS pair once,
 // and one more shuffle swaps the results.  Updates are applied in pair order (0 then 1).
-template <class L, int MODEL, bool ATTR>
+template <class L, int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const float (&x0)[L::NE], const float (&x1)[L::NE],
                                              bool v0, bool v1, float lr, float sd,
@@ -318,7 +339,7 @@ __device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&
     keep += __shfl_xor_sync(kFull, hi ? p0 : p1, H);
 #pragma unroll
     for (int off = H / 2; off >= 1; off >>= 1) keep += __shfl_xor_sync(kFull, keep, off);
-    const float mine = pair_scalar<MODEL, ATTR>(keep, lr, sd, lut);
+    const float mine = pair_scalar<MODEL, ATTR, LS>(keep, lr, sd, lut);
     const float other = __shfl_xor_sync(kFull, mine, H);
     const float s0 = hi ? other : mine, s1 = hi ? mine : other;
     pair_apply<L, MODEL, ATTR>(acc, x0, d0, s0, v0, lr);
@@ -330,10 +351,11 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_s
 // Every group gathers its own `cnt` rows named by idx[0..cnt) (in order) and folds them into
 // its acc.  Indices are fetched LPR at a time per group (coalesced) and broadcast inside the
 // group by shuffle; U row loads per group (G*U per warp) are in flight.
-template <class L, int MODEL, bool ATTR>
+template <class L, int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const uint32_t* __restrict__ idx, uint32_t cnt,
-                                             uint32_t self, const BatchParams& p, float sd, int l) {
+                                             uint32_t self, const BatchParams& p, float sd, int l,
+                                             const float* __restrict__ lut) {
     constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
     const float* const Xlo = p.Xlo;
@@ -344,6 +366,20 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
         const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
         const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
         const uint32_t mine = (uint32_t)l < nb ? __ldg(idx + base + l) : self;
+        if (L::kBulk && p.prefetch) {
+            // the rows of this index block are needed over the next nb/U iterations: start pulling
+            // them into L2 now so that later iterations pay L2 latency instead of DRAM latency
+            const float* prow = ((uint64_t)mine < split ? Xlo : Xhi) + (size_t)mine * rs;
+            if (p.prefetch == 1) {
+                if ((uint32_t)l < nb) bulk_prefetch_l2(prow, (uint32_t)(rs * sizeof(float)));
+            } else {
+                if ((uint32_t)l < nb) {
+#pragma unroll
+                    for (uint32_t ln = 0; ln < (uint32_t)(rs * sizeof(float)); ln += 128)
+                        line_prefetch_l2(reinterpret_cast<const char*>(prow) + ln);
+                }
+            }
+        }
         for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
             bool valid[U];
@@ -360,12 +396,12 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
             if (U % 2 == 0) {
 #pragma unroll
                 for (int u = 0; u < U; u += 2)
-                    pair2_update<L, MODEL, ATTR>(acc, xi, rows[u], rows[u + 1 < U ? u + 1 : u], valid[u],
-                                                 valid[u + 1 < U ? u + 1 : u], p.lr, sd, p.lut, l);
+                    pair2_update<L, MODEL, ATTR, LS>(acc, xi, rows[u], rows[u + 1 < U ? u + 1 : u], valid[u],
+                                                     valid[u + 1 < U ? u + 1 : u], p.lr, sd, lut, l);
             } else {
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    pair_update<L, MODEL, ATTR>(acc, xi, rows[u], valid[u], p.lr, sd, p.lut);
+                    pair_update<L, MODEL, ATTR, LS>(acc, xi, rows[u], valid[u], p.lr, sd, lut);
             }
         }
     }
@@ -373,9 +409,10 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
 
 // G work items, one per group: items t_base .. t_base+G-1 (groups past n_items idle).
 // s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
-template <class L, int MODEL>
+template <class L, int MODEL, bool LS>
 __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_base, const float* s_neg,
-                                              uint64_t* neg_bar, uint32_t neg_parity, int lane) {
+                                              uint64_t* neg_bar, uint32_t neg_parity, int lane,
+                                              const float* __restrict__ lut) {
     constexpr int NE = L::NE, LPR = L::LPR;
     const int g = lane / LPR, l = lane % LPR;
     const size_t rs = L::stride(p.dim);
@@ -408,9 +445,9 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
     for (int k = 0; k < NE; k++) acc[k] = start_at_xi ? xi[k] : 0.f;
 
     if (MODEL == kWalk)
-        gather_pairs<L, MODEL, true>(acc, xi, p.walks + (size_t)v * kWalkLen, active ? kWalkLen : 0, v, p, sd, l);
+        gather_pairs<L, MODEL, true, LS>(acc, xi, p.walks + (size_t)v * kWalkLen, active ? kWalkLen : 0, v, p, sd, l, lut);
     else
-        gather_pairs<L, MODEL, true>(acc, xi, p.colids + it.e0, len, v, p, sd, l);
+        gather_pairs<L, MODEL, true, LS>(acc, xi, p.colids + it.e0, len, v, p, sd, l, lut);
 
     // split rows: publish this chunk's partial sum; the last chunk to arrive folds all of them in
     // chunk order (deterministic) and finishes the row.
@@ -458,16 +495,16 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
             float r0[NE], r1[NE];
             L::load_s(r0, s_neg + (size_t)q * rs, l, p.dim);
             L::load_s(r1, s_neg + (size_t)(q + 1) * rs, l, p.dim);
-            pair2_update<L, MODEL, false>(acc, xi, r0, r1, finish, finish, p.lr, sd, p.lut, l);
+            pair2_update<L, MODEL, false, LS>(acc, xi, r0, r1, finish, finish, p.lr, sd, lut, l);
         }
         if (q < p.s) {
             float row[NE];
             L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
-            pair_update<L, MODEL, false>(acc, xi, row, finish, p.lr, sd, p.lut);
+            pair_update<L, MODEL, false, LS>(acc, xi, row, finish, p.lr, sd, lut);
         }
     } else {
         const uint32_t* nidx = p.neg + ((p.bs_mode && active) ? (size_t)((uint64_t)v - p.lo) : 0);
-        gather_pairs<L, MODEL, false>(acc, xi, nidx, finish ? p.s : 0u, v, p, sd, l);
+        gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, sd, l, lut);
     }
     if (finish) {
         if (MODEL == kTDist || is_chunk) {
@@ -479,43 +516,62 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
 }
 
 // Stage the minibatch's s shared negative rows in shared memory (TMA bulk copies issued by
-// lanes 0..s-1 of warp 0, completion on one mbarrier).
+// the lanes of warp 0, completion on the CTA's mbarrier whose expected byte count the caller set).
 template <class L>
 __device__ __forceinline__ void stage_negatives(const BatchParams& p, float* s_neg, uint64_t* bar) {
     const size_t rs = L::stride(p.dim);
     const uint32_t row_bytes = (uint32_t)(rs * sizeof(float));
-    if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) mbar_expect_tx(bar, row_bytes * p.s);
-        __syncwarp();
-        for (uint32_t q = threadIdx.x; q < p.s; q += 32) {
-            const uint32_t j = __ldg(p.neg + q);
-            const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
-            bulk_g2s(s_neg + (size_t)q * rs, src, row_bytes, bar);
-        }
+    for (uint32_t q = threadIdx.x; q < p.s; q += 32) {      // called by warp 0 after expect_tx
+        const uint32_t j = __ldg(p.neg + q);
+        const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
+        bulk_g2s(s_neg + (size_t)q * rs, src, row_bytes, bar);
     }
 }
 
 // ------------------------------------------------------------------ kernels ------------
-// One launch per minibatch; one group of lanes per item; the hardware CTA scheduler balances
-// the load (items are ordered hub chunks first, then rows by descending degree class, so the
-// groups of a warp get items of similar length).
-template <class L, int MODEL>
+// One launch per minibatch.  PERSIST = false: one group of lanes per item and one pass per CTA,
+// the hardware CTA scheduler balances the load.  PERSIST = true: the grid is sized to the
+// machine (SMs x resident CTAs), every warp strides over the item list (items are ordered hub
+// chunks first, then rows by descending degree class, so round-robin is longest-first), and
+// the per-CTA staging -- the minibatch's negative rows and, for the sigmoid models, the LUT,
+// all by TMA bulk copies on one mbarrier -- is paid once per CTA instead of once per 16 items.
+template <class L, int MODEL, bool PERSIST>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, L::MINB)
 force_batch_kernel(const BatchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool LS = PERSIST && MODEL != kTDist && L::kBulk;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float* s_neg = nullptr;
-    if (L::kBulk && p.neg_in_smem) {
-        s_neg = reinterpret_cast<float*>(smem_raw + 128);
+    const bool negs = L::kBulk && p.neg_in_smem;
+    float* s_neg = negs ? reinterpret_cast<float*>(smem_raw + 128) : nullptr;
+    const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
+    const float* lut = p.lut;
+    if (negs || LS) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
-        stage_negatives<L>(p, s_neg, bar);
+        if (threadIdx.x < 32) {
+            const uint32_t lut_bytes = LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u;
+            if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes + lut_bytes);
+            __syncwarp();
+            if (negs) stage_negatives<L>(p, s_neg, bar);
+            if (LS && threadIdx.x == 31) bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, lut_bytes, bar);
+        }
+        if (LS) {
+            lut = reinterpret_cast<const float*>(smem_raw + 128 + neg_bytes);
+            mbar_wait(bar, 0);      // the table is needed by the first attractive pair
+        }
     }
     const int lane = threadIdx.x & 31;
-    const uint32_t t_base = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * L::G;
-    if (t_base < p.n_items) process_items<L, MODEL>(p, t_base, s_neg, bar, 0, lane);
+    const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (PERSIST) {
+        const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
+        for (uint32_t t_base = gw * L::G; t_base < p.n_items; t_base += stride)
+            process_items<L, MODEL, LS>(p, t_base, s_neg, bar, 0, lane, lut);
+    } else {
+        const uint32_t t_base = gw * L::G;
+        if (t_base < p.n_items) process_items<L, MODEL, LS>(p, t_base, s_neg, bar, 0, lane, lut);
+    }
     // the CTA's shared memory must stay allocated until the bulk copies have landed
-    if (s_neg != nullptr) mbar_wait(bar, 0);
+    if (negs || LS) mbar_wait(bar, 0);
 }
 
 // Counter-based draw for the device walk sampler (host mirror: oracle f2vo_counter_rand).

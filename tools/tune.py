@@ -26,7 +26,9 @@ def main():
     ap.add_argument("--chunks", default="64")
     ap.add_argument("--modes", default="0")
     ap.add_argument("--negsmem", default="1")
-    ap.add_argument("--pars", default="0")
+    ap.add_argument("--pars", default="9472")
+    ap.add_argument("--prefetch", default="0")
+    ap.add_argument("--persist", default="0")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -46,30 +48,36 @@ def main():
     for B, var, ch, mode, ns, par in itertools.product([int(x) for x in a.batches.split(",")], [int(x) for x in a.variants.split(",")],
                                                        [int(x) for x in a.chunks.split(",")], [int(x) for x in a.modes.split(",")],
                                                        [int(x) for x in a.negsmem.split(",")], [int(x) for x in a.pars.split(",")]):
-        neg = g.epoch_negatives(a.model, n, B, 5, a.bs).copy()
-        eng.set_negatives(neg)
-        eng.set_option("variant", var)
-        eng.set_option("neg_smem", ns)
-        try:
-            eng.set_option("par", par)
-        except F.F2VError:
-            pass
-        try:
-            eng.set_epoch_mode(mode)
-        except F.F2VError as ex:
-            print("mode", mode, "unavailable:", ex)
-            continue
-        eng.run_epoch(a.model, B, 5, a.bs, 0.02, ch)   # warm (plan build)
-        eng.sync()
-        ms = []
-        for _ in range(a.reps):
-            eng.run_epoch(a.model, B, 5, a.bs, 0.02, ch)
-            ms.append(eng.last_epoch_ms())
-        best = min(ms)
-        row = {"B": B, "variant": var, "chunk": ch, "mode": mode, "neg_smem": ns, "par": par, "ms": best, "ms_all": ms,
-               "Gpairs_s": pairs / best / 1e6, "GBs": byts / best / 1e6, "frac": byts / best / 1e6 / 6553.3}
-        rows.append(row)
-        print(json.dumps(row), flush=True)
+      for pf, ps in itertools.product([int(x) for x in a.prefetch.split(",")], [int(x) for x in a.persist.split(",")]):
+            neg = g.epoch_negatives(a.model, n, B, 5, a.bs).copy()
+            eng.set_negatives(neg)
+            eng.set_option("variant", var)
+            eng.set_option("neg_smem", ns)
+            try:
+                eng.set_option("prefetch", pf)
+                eng.set_option("persist", ps)
+            except F.F2VError:
+                pass
+            try:
+                eng.set_option("par", par)
+            except F.F2VError:
+                pass
+            try:
+                eng.set_epoch_mode(mode)
+            except F.F2VError as ex:
+                print("mode", mode, "unavailable:", ex)
+                continue
+            eng.run_epoch(a.model, B, 5, a.bs, 0.02, ch)   # warm (plan build)
+            eng.sync()
+            ms = []
+            for _ in range(a.reps):
+                eng.run_epoch(a.model, B, 5, a.bs, 0.02, ch)
+                ms.append(eng.last_epoch_ms())
+            best = min(ms)
+            row = {"B": B, "variant": var, "chunk": ch, "mode": mode, "neg_smem": ns, "par": par, "prefetch": pf, "persist": ps, "ms": best, "ms_all": ms,
+                   "Gpairs_s": pairs / best / 1e6, "GBs": byts / best / 1e6, "frac": byts / best / 1e6 / 6553.3}
+            rows.append(row)
+            print(json.dumps(row), flush=True)
     if a.out:
         json.dump(rows, open(a.out, "w"), indent=1)
     eng.close()
