@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--mode", type=int, default=0, help="engine epoch mode (0 per-minibatch launches, 1 persistent)")
     ap.add_argument("--variant", type=int, default=3, help="d=128 kernel lane layout (f2v_set_option)")
     ap.add_argument("--neg-smem", type=int, default=1)
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="N>1 exchange: peer = stores into the peers' replicas fused into the force kernel; "
+                         "nccl = all-gather per minibatch (baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra-batches", default="256,4096,16384", help="comma list of additional batch sizes to report")
@@ -271,10 +274,14 @@ def run_ours(a):
         eng.set_epoch_mode(a.mode)
     eng.set_option("variant", a.variant)
     eng.set_option("neg_smem", a.neg_smem)
-    if world > 1:
+    if world > 1 and a.comm == "nccl":
         ids = [F.Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         eng.comm_init(ids[0], rank, world)
+    elif world > 1:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, eng.comm_peer_export())
+        eng.comm_peer_init(blobs, rank, world)
     if a.model != 5:
         eng.set_lut()
     eng.set_embeddings(X0.numpy())
@@ -365,10 +372,14 @@ def run_ours(a):
                                  % (n * a.dim * 4 / 2**20, nnz * 4 / 2**20),
                            "init": "glibc-compatible srand(1) stream (reference order)",
                            "parallelism": "replicated table, minibatch split over %d rank(s)%s" %
-                                          (world, ", NCCL all-gather per minibatch" if world > 1 else "")},
+                                          (world, "" if world == 1 else (", NCCL all-gather per minibatch" if a.comm == "nccl" else
+                                                      ", rows stored into the peers' replicas from the force kernel "
+                                                      "(NVLink peer stores + flag barrier per minibatch)"))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "epoch_s": epoch_s, "extra": extra}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()                  # nobody unmaps a table a peer may still be storing into
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +387,12 @@ def run_ours(a):
 
 def main():
     a = parse()
+    # stdout carries exactly one JSON line: anything libraries print on fd 1 (NCCL's version banner,
+    # the reference's progress lines) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -6,6 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 TDIST, SIGMOID, WALK = 5, 6, 7
 WALKLEN = 5
 LUT_SIZE = 2048
+PEER_BLOB = 256
 
 ENGINE_SYMBOLS = [
     "f2v_last_error", "f2v_abi_version", "f2v_device_count", "f2v_create", "f2v_destroy",
@@ -14,7 +15,7 @@ ENGINE_SYMBOLS = [
     "f2v_set_walks",
     "f2v_get_walks", "f2v_sample_walks", "f2v_step", "f2v_run_epoch", "f2v_run_epoch_host",
     "f2v_set_epoch_mode", "f2v_set_option", "f2v_launch_count", "f2v_last_epoch_ms", "f2v_comm_unique_id",
-    "f2v_comm_init",
+    "f2v_comm_init", "f2v_comm_peer_export", "f2v_comm_peer_init",
 ]
 HOST_SYMBOLS = [
     "f2v_rng_create", "f2v_rng_destroy", "f2v_rng_next", "f2v_init_embeddings", "f2v_build_lut",
@@ -79,6 +80,8 @@ def lib():
     L.f2v_last_epoch_ms.argtypes = [vp, C.POINTER(f32)]
     L.f2v_comm_unique_id.argtypes = [vp]
     L.f2v_comm_init.argtypes = [vp, vp, i32, i32]
+    L.f2v_comm_peer_export.argtypes = [vp, vp]
+    L.f2v_comm_peer_init.argtypes = [vp, vp, i32, i32]
     # host side
     L.f2v_rng_create.argtypes = [u32]
     L.f2v_rng_create.restype = vp
@@ -96,7 +99,7 @@ def lib():
     L.f2v_write_embd.argtypes = [C.c_char_p, vp, u64, u32]
     L.f2v_write_mtx.argtypes = [C.c_char_p, u64, vp, vp]
     L.f2v_rmat_csr.argtypes = [i32, i32, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
-    L.f2v_plan_build.argtypes = [vp, u64, u64, u32, u32, u32, i32, i32, i32, C.POINTER(u64), C.POINTER(vp),
+    L.f2v_plan_build.argtypes = [vp, u64, u64, u32, u32, u32, i32, i32, i32, i32, C.POINTER(u64), C.POINTER(vp),
                                  C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.f2v_train.argtypes = [C.POINTER(TrainArgs), vp, C.POINTER(C.c_double)]
     _lib = L

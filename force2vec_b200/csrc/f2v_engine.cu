@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <new>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 using namespace f2v;
@@ -74,7 +75,7 @@ constexpr int kNcclFloat32 = 7;   // ncclFloat32 in nccl.h's ncclDataType_t
 struct Plan {
     uint32_t batch = 0, chunk = 0, par = 0;
     bool walk = false;
-    int rank = 0, world = 1;
+    int rank = 0, world = 1, assign = 0;
     uint64_t first_row = 0, nrows = 0;      // row range covered (whole table for epochs)
     uint64_t nb = 0;
     std::vector<uint64_t> item_ptr;         // nb+1 offsets into items / hub
@@ -120,7 +121,31 @@ struct f2v_engine {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     int sm_count = 0;
+    // peer-store exchange (f2v_comm_peer_*): the other ranks' tables and flag pages, mapped
+    // through CUDA IPC (other processes) or used directly (engines of this process)
+    bool peer_mode = false;
+    float* peerX[kMaxWorld][2] = {};
+    uint64_t* peer_flags[kMaxWorld] = {};    // base of rank r's flag page
+    bool peer_ipc[kMaxWorld] = {};           // mapping opened with cudaIpcOpenMemHandle
+    uint64_t* d_flags = nullptr;             // local flag page, kMaxWorld * kFlagStride u64
+    uint32_t* d_done = nullptr;
+    uint64_t step_id = 0;                    // minibatch steps published so far (same on every rank)
+    int peer_debug = 0;                      // timing probes only: 1 = no peer row stores, 2 = no flag barrier
+    int peer_sig = 1;                        // 1: a 1-CTA kernel after the force kernel publishes the step (default);
+                                             // 0: the force kernel's last CTA does (a system fence per CTA: measured slower)
 };
+
+// What a rank publishes for the peer-store exchange (f2v_comm_peer_export): fits F2V_PEER_BLOB.
+struct PeerBlob {
+    uint32_t magic;
+    int32_t device;
+    uint64_t pid;
+    uint64_t n, dim, cur;
+    uint64_t ptr[3];                         // X[0], X[1], flags (valid inside process `pid`)
+    cudaIpcMemHandle_t h[3];
+};
+static_assert(sizeof(PeerBlob) <= F2V_PEER_BLOB, "PeerBlob must fit the ABI's blob size");
+constexpr uint32_t kPeerMagic = 0x46325650u;
 
 static int ensure(void** p, uint64_t* cap, uint64_t need_bytes) {
     if (*cap >= need_bytes && *p) return F2V_OK;
@@ -135,12 +160,12 @@ static int ensure(void** p, uint64_t* cap, uint64_t need_bytes) {
 // Upload the host plan (f2v_plan.hpp) for rows [first_row, first_row+nrows) and size the
 // hub-row partial buffers.  Cached on (batch, chunk, walk, rank, world, range).
 static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrows, uint32_t batch,
-                      uint32_t chunk, uint32_t par, bool walk, int rank, int world) {
+                      uint32_t chunk, uint32_t par, bool walk, int rank, int world, int assign) {
     if (pl.d_items && pl.batch == batch && pl.chunk == chunk && pl.par == par && pl.walk == walk && pl.rank == rank &&
-        pl.world == world && pl.first_row == first_row && pl.nrows == nrows)
+        pl.world == world && pl.assign == assign && pl.first_row == first_row && pl.nrows == nrows)
         return F2V_OK;
     HostPlan hp;
-    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, par, walk, rank, world, hp);
+    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, par, walk, rank, world, assign, hp);
     const uint64_t nb = hp.nb, total = hp.items.size();
     std::vector<Item>& items = hp.items;
     std::vector<HubInfo>& hub = hp.hub;
@@ -172,6 +197,7 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         e->slots_cap = slots;
     }
     pl.batch = batch; pl.chunk = chunk; pl.par = par; pl.walk = walk; pl.rank = rank; pl.world = world;
+    pl.assign = assign;
     pl.first_row = first_row; pl.nrows = nrows; pl.nb = nb;
     pl.item_ptr.swap(item_ptr);
     pl.n_hub.swap(n_hub);
@@ -323,6 +349,13 @@ int f2v_destroy(f2v_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (int r = 0; r < kMaxWorld; r++) {
+        if (!e->peer_ipc[r]) continue;
+        cudaIpcCloseMemHandle(e->peerX[r][0]);
+        cudaIpcCloseMemHandle(e->peerX[r][1]);
+        cudaIpcCloseMemHandle(e->peer_flags[r]);
+    }
+    cudaFree(e->d_flags); cudaFree(e->d_done);
     cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_X[0]); cudaFree(e->d_X[1]);
     cudaFree(e->d_lut); cudaFree(e->d_neg); cudaFree(e->d_walks); cudaFree(e->d_stage);
     cudaFree(e->d_partials); cudaFree(e->d_counters);
@@ -475,7 +508,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     if (s > 0 && !neg_idx) return fail(F2V_ERR_ARG, "neg_idx is null");
     r = f2v_set_negatives(e, neg_idx, neg_stride(model, nrows, s, bs_mode));
     if (r) return r;
-    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 128, (uint32_t)e->par, model == F2V_WALK, 0, 1);
+    r = build_plan(e, e->step_plan, first_row, nrows, nrows, 128, (uint32_t)e->par, model == F2V_WALK, 0, 1, 0);
     if (r) return r;
     uint64_t cap_bytes = e->stage_cap;
     r = ensure((void**)&e->d_stage, &cap_bytes, sizeof(float) * (uint64_t)nrows * e->dim);
@@ -506,7 +539,8 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
     int r = check_model(e, model, s, bs_mode);
     if (r) return r;
     if (batch == 0) return fail(F2V_ERR_ARG, "batch must be > 0");
-    if (e->world > 1 && batch % e->world) return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
+    if (e->world > 1 && !e->peer_mode && batch % e->world)
+        return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
     CU(cudaSetDevice(e->device));
     if (chunk == 0) chunk = 128;
     const uint64_t nb = (e->n + batch - 1) / batch;
@@ -515,7 +549,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
         return fail(F2V_ERR_STATE, "negative stream too short: have %llu (offset %llu), epoch needs %llu",
                     (unsigned long long)e->neg_count, (unsigned long long)e->neg_off, (unsigned long long)(nb * W));
     // tables: the all-gather works on whole minibatches, so pad the row count to nb*batch
-    const uint64_t rows_needed = e->world > 1 ? nb * batch : e->n;
+    const uint64_t rows_needed = (e->world > 1 && !e->peer_mode) ? nb * batch : e->n;
     if (e->rows_alloc < rows_needed) {
         CU(cudaStreamSynchronize(e->stream));
         float* nx = nullptr;
@@ -531,7 +565,8 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
         CU(cudaMalloc((void**)&e->d_X[1 - e->cur], sizeof(float) * e->rows_alloc * e->dim));
         CU(cudaMemsetAsync(e->d_X[1 - e->cur], 0, sizeof(float) * e->rows_alloc * e->dim, e->stream));
     }
-    r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world);
+    r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world,
+                   e->peer_mode ? kAssignBalanced : kAssignSlices);
     if (r) return r;
     const Plan& pl = e->epoch_plan;
     float* Xold = e->d_X[e->cur];
@@ -544,6 +579,18 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
     p.lr = lr; p.variant = e->variant; p.prefetch = e->prefetch;
     const uint64_t slice = batch / (uint64_t)e->world;
+    if (e->peer_mode) {
+        p.n_peers = (e->peer_debug & 2) ? 0u : (uint32_t)(e->world - 1);
+        p.n_store = (e->peer_debug & 1) ? 0u : (uint32_t)(e->world - 1);
+        p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
+        p.flags = e->d_flags; p.done = e->d_done;
+        for (int r = 0, k = 0; r < e->world; r++) {
+            if (r == e->rank) continue;
+            p.peer_out[k] = e->peerX[r][1 - e->cur];
+            p.peer_flag[k] = e->peer_flags[r] + (size_t)e->rank * kFlagStride;
+            k++;
+        }
+    }
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
         p.hub = pl.d_hub + pl.item_ptr[b];
@@ -552,16 +599,43 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
         p.lo = b * batch;
         p.split = b * batch;
         p.neg = e->d_neg + e->neg_off + b * W;
+        if (e->peer_mode) {
+            // minibatch b reads rows its peers stored during step_id (minibatch b-1); it publishes step_id+1
+            p.wait_step = (e->peer_debug & 2) ? 0 : e->step_id;
+            p.signal_step = ++e->step_id;
+        }
         if (p.n_items) {
+            const uint64_t sig = p.signal_step;
+            if (e->peer_mode && e->peer_sig) p.signal_step = 0;
             CU(launch_batch(model, p, e->stream, e->sm_count, e->persist));
             e->launches++;
+            if (e->peer_mode && e->peer_sig && p.n_peers) {
+                // the force kernel has drained (all its peer stores are performed): publish the step
+                BatchParams q = p;
+                q.wait_step = 0; q.signal_step = sig;
+                peer_sync_kernel<<<1, 32, 0, e->stream>>>(q);
+                CU(cudaGetLastError());
+                e->launches++;
+            }
+        } else if (e->peer_mode) {
+            peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
+            CU(cudaGetLastError());
+            e->launches++;
         }
-        if (e->world > 1) {
+        if (e->world > 1 && !e->peer_mode) {
             // exchange the updated slices before the next minibatch reads them
             float* base = Xnew + b * batch * e->dim;
             NC(g_nccl.AllGather(base + (uint64_t)e->rank * slice * e->dim, base, slice * e->dim,
                                 kNcclFloat32, e->comm, e->stream));
         }
+    }
+    if (e->peer_mode) {
+        // the replica is complete once every peer has published the epoch's last step
+        p.wait_step = (e->peer_debug & 2) ? 0 : e->step_id;
+        p.signal_step = 0;
+        peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
+        CU(cudaGetLastError());
+        e->launches++;
     }
     CU(cudaEventRecord(e->ev1, e->stream));
     e->ev_valid = true;
@@ -601,6 +675,8 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "par")) e->par = (int)value;
     else if (!strcmp(name, "prefetch")) e->prefetch = (int)value;
     else if (!strcmp(name, "persist")) e->persist = value != 0;
+    else if (!strcmp(name, "peer_debug")) e->peer_debug = (int)value;
+    else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }
@@ -629,7 +705,7 @@ int f2v_comm_unique_id(void* id128) {
 int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world) {
     if (!e || !id128) return fail(F2V_ERR_ARG, "null argument");
     if (world < 1 || rank < 0 || rank >= world) return fail(F2V_ERR_ARG, "bad rank/world");
-    if (e->comm) return fail(F2V_ERR_STATE, "communicator already initialised");
+    if (e->comm || e->peer_mode) return fail(F2V_ERR_STATE, "communicator already initialised");
     int r = nccl_load();
     if (r) return r;
     CU(cudaSetDevice(e->device));
@@ -638,6 +714,81 @@ int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world) {
     NC(g_nccl.CommInitRank(&e->comm, world, id, rank));
     e->rank = rank;
     e->world = world;
+    return F2V_OK;
+}
+
+int f2v_comm_peer_export(f2v_engine* e, void* blob) {
+    if (!e || !blob) return fail(F2V_ERR_ARG, "null argument");
+    if (e->world > 1) return fail(F2V_ERR_STATE, "communicator already initialised");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (!e->d_X[1 - e->cur]) {
+        CU(cudaMalloc((void**)&e->d_X[1 - e->cur], sizeof(float) * e->rows_alloc * e->dim));
+        CU(cudaMemset(e->d_X[1 - e->cur], 0, sizeof(float) * e->rows_alloc * e->dim));
+    }
+    if (!e->d_flags) {
+        CU(cudaMalloc((void**)&e->d_flags, sizeof(uint64_t) * kMaxWorld * kFlagStride));
+        CU(cudaMemset(e->d_flags, 0, sizeof(uint64_t) * kMaxWorld * kFlagStride));
+        CU(cudaMalloc((void**)&e->d_done, sizeof(uint32_t) * 32));
+        CU(cudaMemset(e->d_done, 0, sizeof(uint32_t) * 32));
+    }
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kPeerMagic; b.device = e->device; b.pid = (uint64_t)getpid();
+    b.n = e->n; b.dim = e->dim; b.cur = (uint64_t)e->cur;
+    void* ptrs[3] = {e->d_X[0], e->d_X[1], e->d_flags};
+    for (int k = 0; k < 3; k++) {
+        b.ptr[k] = (uint64_t)(uintptr_t)ptrs[k];
+        CU(cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
+    }
+    memset(blob, 0, F2V_PEER_BLOB);
+    memcpy(blob, &b, sizeof(b));
+    return F2V_OK;
+}
+
+int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
+    if (!e || !blobs) return fail(F2V_ERR_ARG, "null argument");
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+        return fail(F2V_ERR_ARG, "bad rank/world (peer exchange supports up to %d ranks)", kMaxWorld);
+    if (e->comm || e->peer_mode) return fail(F2V_ERR_STATE, "communicator already initialised");
+    if (!e->d_flags) return fail(F2V_ERR_STATE, "call f2v_comm_peer_export first");
+    CU(cudaSetDevice(e->device));
+    const uint64_t me = (uint64_t)getpid();
+    for (int r = 0; r < world; r++) {
+        PeerBlob b;
+        memcpy(&b, (const char*)blobs + (size_t)r * F2V_PEER_BLOB, sizeof(b));
+        if (b.magic != kPeerMagic) return fail(F2V_ERR_ARG, "blob %d is not a peer blob", r);
+        if (b.n != e->n || b.dim != e->dim) return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
+        if (b.cur != (uint64_t)e->cur) return fail(F2V_ERR_STATE, "rank %d is at a different table parity", r);
+        if (r == rank) {
+            if (b.ptr[0] != (uint64_t)(uintptr_t)e->d_X[0]) return fail(F2V_ERR_ARG, "blob %d is not this engine's", r);
+            continue;
+        }
+        if (b.pid == me) {
+            // an engine of this process on another device: plain peer access
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, e->device, b.device));
+            if (!can) return fail(F2V_ERR_CUDA, "device %d cannot access device %d", e->device, b.device);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(F2V_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+            cudaGetLastError();
+            e->peerX[r][0] = (float*)(uintptr_t)b.ptr[0];
+            e->peerX[r][1] = (float*)(uintptr_t)b.ptr[1];
+            e->peer_flags[r] = (uint64_t*)(uintptr_t)b.ptr[2];
+        } else {
+            void* m[3] = {nullptr, nullptr, nullptr};
+            for (int k = 0; k < 3; k++) CU(cudaIpcOpenMemHandle(&m[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
+            e->peerX[r][0] = (float*)m[0];
+            e->peerX[r][1] = (float*)m[1];
+            e->peer_flags[r] = (uint64_t*)m[2];
+            e->peer_ipc[r] = true;
+        }
+    }
+    e->rank = rank;
+    e->world = world;
+    e->peer_mode = world > 1;
+    e->step_id = 0;
     return F2V_OK;
 }
 

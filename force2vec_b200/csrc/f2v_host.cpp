@@ -379,13 +379,13 @@ extern "C" int f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t*
 
 // ------------------------------------------------------------------ plan ---------------
 extern "C" int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64_t nrows, uint32_t batch,
-                              uint32_t chunk, uint32_t par, int walk, int rank, int world, uint64_t* nb,
+                              uint32_t chunk, uint32_t par, int walk, int rank, int world, int assign, uint64_t* nb,
                               uint64_t** item_ptr, uint32_t** n_hub, void** items, void** hub) {
     if (!rowptr || !nb || !item_ptr || !n_hub || !items || !hub || batch == 0 || world < 1 || rank < 0 ||
-        rank >= world || chunk == 0)
+        rank >= world || chunk == 0 || assign < 0 || assign > 1)
         return F2V_ERR_ARG;
     f2v::HostPlan hp;
-    f2v::build_host_plan(rowptr, first_row, nrows, batch, chunk, par, walk != 0, rank, world, hp);
+    f2v::build_host_plan(rowptr, first_row, nrows, batch, chunk, par, walk != 0, rank, world, assign, hp);
     const size_t total = hp.item_ptr[hp.nb];
     *nb = hp.nb;
     *item_ptr = (uint64_t*)malloc(sizeof(uint64_t) * (hp.nb + 1));

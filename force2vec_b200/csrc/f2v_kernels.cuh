@@ -37,6 +37,8 @@ constexpr int kLutSize = 2048;
 constexpr int kLutAlloc = 2052;          // padded to a multiple of 16 bytes
 constexpr int kWarpsPerCta = 8;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxWorld = 8;             // ranks of one NVSwitch domain
+constexpr int kFlagStride = 16;          // u64 per exchange flag: one 128-byte line each
 
 struct BatchParams {
     const Item* items;
@@ -62,6 +64,17 @@ struct BatchParams {
     int variant;          // layout variant of the d=128 kernels (tuning knob)
     int prefetch;         // 0 none, 1 TMA bulk L2 prefetch of a whole index block's rows, 2 per-line L2 prefetch
     float lr;
+    // ---- peer-store exchange (multi-GPU): every finished row is also stored into the other
+    // ranks' replicas of `out` over NVLink; one flag per (source rank) and minibatch step.
+    uint32_t n_peers;                    // 0 = single GPU / NCCL exchange
+    uint32_t rank, world;
+    float* peer_out[kMaxWorld - 1];      // the peers' copies of `out` (same row indexing)
+    uint64_t* peer_flag[kMaxWorld - 1];  // this rank's flag slot in each peer's flag page
+    const uint64_t* flags;               // local flag page: flags[r * kFlagStride] written by rank r
+    uint64_t wait_step;                  // before reading Xlo: every peer's flag >= wait_step (0 = no wait)
+    uint64_t signal_step;                // after the last CTA's stores: peers' flags := signal_step
+    uint32_t* done;                      // CTA arrival counter of the launch
+    uint32_t n_store;                    // peers that receive row stores (= n_peers; 0 only in timing probes)
 };
 
 // ------------------------------------------------------------------ PTX helpers --------
@@ -91,6 +104,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t byte
 }
 __device__ __forceinline__ void line_prefetch_l2(const void* gmem) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
+}
+// System-scope flag traffic of the peer-store exchange.
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -511,7 +533,37 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
 #pragma unroll
             for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(xi[k], acc[k]);   // X[i] += delta (:629-639)
         }
-        L::store_g(p.out + (size_t)((uint64_t)v - p.out_base) * rs, acc, l, p.dim);
+        const size_t off = (size_t)((uint64_t)v - p.out_base) * rs;
+        L::store_g(p.out + off, acc, l, p.dim);
+        // multi-GPU: the exchange is fused here -- the row goes straight into every peer's replica
+        for (uint32_t r = 0; r < p.n_store; r++) L::store_g(p.peer_out[r] + off, acc, l, p.dim);
+    }
+}
+
+// Exchange barrier, entry side: before any row of the next table is read, every peer must have
+// published the minibatch step that wrote it.  Threads 0..world-1 poll one flag each.
+__device__ __forceinline__ void peer_wait(const BatchParams& p) {
+    if (p.wait_step == 0) return;
+    if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+        const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
+        while (ld_acquire_sys(f) < p.wait_step) {}
+    }
+    __syncthreads();
+}
+
+// Exchange barrier, exit side: the last CTA of the launch to finish its (local and peer) stores
+// publishes signal_step in every peer's flag page.  Called by all threads of the CTA.
+__device__ __forceinline__ void peer_signal(const BatchParams& p) {
+    if (p.n_peers == 0 || p.signal_step == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const uint32_t old = atomicAdd(p.done, 1u);
+        if (old == gridDim.x - 1) {
+            *p.done = 0;                         // re-arm for the next launch (stream-ordered)
+            __threadfence_system();
+            for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], p.signal_step);
+        }
     }
 }
 
@@ -545,12 +597,14 @@ force_batch_kernel(const BatchParams p) {
     float* s_neg = negs ? reinterpret_cast<float*>(smem_raw + 128) : nullptr;
     const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
     const float* lut = p.lut;
+    peer_wait(p);
     if (negs || LS) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
         if (threadIdx.x < 32) {
             const uint32_t lut_bytes = LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u;
             if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes + lut_bytes);
+            if (p.wait_step) fence_proxy_async();   // rows written by peers (generic proxy) are read by TMA next
             __syncwarp();
             if (negs) stage_negatives<L>(p, s_neg, bar);
             if (LS && threadIdx.x == 31) bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, lut_bytes, bar);
@@ -572,6 +626,14 @@ force_batch_kernel(const BatchParams p) {
     }
     // the CTA's shared memory must stay allocated until the bulk copies have landed
     if (negs || LS) mbar_wait(bar, 0);
+    peer_signal(p);
+}
+
+// A launch with no rows on this rank still takes part in the exchange barrier; the epoch ends with
+// a wait for every peer's last step (then this replica is complete).  One CTA.
+__global__ void peer_sync_kernel(const BatchParams p) {
+    peer_wait(p);
+    peer_signal(p);
 }
 
 // Counter-based draw for the device walk sampler (host mirror: oracle f2vo_counter_rand).

@@ -46,38 +46,88 @@ inline void slice_range(uint64_t first_row, uint64_t nrows, uint32_t batch, int 
     hi = std::min(lo + slice, bhi);
 }
 
+// Row ownership on a multi-GPU engine.
+//   kAssignSlices   : minibatch [blo, bhi) cut into `world` contiguous slices (what an all-gather
+//                     of equal-sized blocks needs);
+//   kAssignBalanced : longest-processing-time greedy over the minibatch's rows by cost
+//                     deg + kRowCost (rows by descending degree, each to the least-loaded rank;
+//                     ties by lower vertex id / lower rank), so every rank gets the same number
+//                     of pair updates although R-MAT puts its hubs at the low ids.  Used by the
+//                     peer-store exchange, which has no contiguity requirement.
+// Both are pure functions of (rowptr, batch, world): every rank computes the same partition.
+constexpr int kAssignSlices = 0, kAssignBalanced = 1;
+constexpr uint64_t kRowCost = 6;      // own row + ~5 negatives per vertex
+
+// Rows of minibatch b owned by `rank`, ascending.  world == 1: the whole minibatch.
+inline void owned_rows(const uint64_t* rp, uint64_t first_row, uint64_t nrows, uint32_t batch, int rank, int world,
+                       int assign, bool walk, uint64_t b, std::vector<uint32_t>& rows) {
+    rows.clear();
+    const uint64_t blo = first_row + b * batch, bhi = std::min(blo + (uint64_t)batch, first_row + nrows);
+    if (world == 1 || assign == kAssignSlices) {
+        uint64_t lo, hi;
+        slice_range(first_row, nrows, batch, rank, world, b, lo, hi);
+        rows.reserve(hi - lo);
+        for (uint64_t v = lo; v < hi; v++) rows.push_back((uint32_t)v);
+        return;
+    }
+    const uint64_t m = bhi - blo;
+    if (walk) {                                   // every row costs the same: deal round-robin
+        for (uint64_t k = (uint64_t)rank; k < m; k += (uint64_t)world) rows.push_back((uint32_t)(blo + k));
+        return;
+    }
+    std::vector<uint32_t> order(m);
+    for (uint64_t k = 0; k < m; k++) order[k] = (uint32_t)(blo + k);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) {
+        return rp[a + 1] - rp[a] > rp[c + 1] - rp[c];
+    });
+    std::vector<uint64_t> load((size_t)world, 0);
+    for (uint64_t k = 0; k < m; k++) {
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (load[r] < load[best]) best = r;
+        const uint32_t v = order[k];
+        load[best] += rp[v + 1] - rp[v] + kRowCost;
+        if (best == rank) rows.push_back(v);
+    }
+    std::sort(rows.begin(), rows.end());
+}
+
 // Work plan for rows [first_row, first_row+nrows) cut into minibatches of `batch` rows
 // (minibatch b of the range; for epochs first_row = 0, nrows = n).  Within a minibatch:
 // hub chunks first (rows with more than `chunk` edges, cut into equal chunks), then the
 // remaining rows by descending degree class, so the heaviest items are scheduled first.
-// On a multi-GPU engine only the rank's slice of every minibatch is planned.
+// On a multi-GPU engine only the rows of every minibatch that `rank` owns are planned.
 // `par` > 0 makes the chunk length adaptive per minibatch: chunk_b = clamp(edges_b / par,
-// kMinChunk, chunk), so that a minibatch with little work is still cut into enough items to
-// occupy `par` lane groups in one wave and its critical path (the longest item) stays short.
+// kMinChunk, chunk) with edges_b the edges of the whole minibatch (all ranks), so that a
+// minibatch with little work is still cut into enough items to occupy `par` lane groups in one
+// wave and its critical path (the longest item) stays short.
 inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nrows, uint32_t batch,
-                            uint32_t chunk, uint32_t par, bool walk, int rank, int world, HostPlan& out) {
+                            uint32_t chunk, uint32_t par, bool walk, int rank, int world, int assign, HostPlan& out) {
     const uint64_t nb = (nrows + batch - 1) / batch;
     std::vector<uint64_t> item_ptr(nb + 1, 0);
     std::vector<uint32_t> n_hub(nb, 0), n_slots(nb, 0);
-    auto my_range = [&](uint64_t b, uint64_t& lo, uint64_t& hi) {
-        slice_range(first_row, nrows, batch, rank, world, b, lo, hi);
-    };
-    auto chunk_of_batch = [&](uint64_t lo, uint64_t hi) -> uint64_t {
-        if (par == 0 || hi <= lo) return chunk;
-        const uint64_t edges = rp[hi] - rp[lo];
-        const uint64_t c = (edges + par - 1) / par;
-        return std::min<uint64_t>(chunk, std::max<uint64_t>(std::min<uint64_t>(kMinChunk, chunk), c));
-    };
+    std::vector<uint64_t> chunk_len(nb, chunk);
+    std::vector<std::vector<uint32_t>> mine(nb);
     auto nchunks_of = [&](uint64_t deg, uint64_t ch) -> uint64_t {
         return (!walk && deg > ch) ? (deg + ch - 1) / ch : 1;
     };
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(dynamic, 16)
     for (int64_t b = 0; b < (int64_t)nb; b++) {
-        uint64_t lo, hi, cnt = 0, hubs = 0;
-        my_range((uint64_t)b, lo, hi);
-        const uint64_t ch = chunk_of_batch(lo, hi);
-        uint64_t slots = 0;
-        for (uint64_t v = lo; v < hi; v++) {
+        std::vector<uint32_t>& rows = mine[b];
+        owned_rows(rp, first_row, nrows, batch, rank, world, assign, walk, (uint64_t)b, rows);
+        // the chunk length is a function of the WHOLE minibatch, not of this rank's share: a hub row
+        // is then cut (and its partial sums folded) identically for every world size, which keeps
+        // multi-GPU results bit-identical to the single-GPU run
+        const uint64_t blo = first_row + (uint64_t)b * batch, bhi = std::min(blo + (uint64_t)batch, first_row + nrows);
+        const uint64_t edges = rp[bhi] - rp[blo];
+        uint64_t ch = chunk;
+        if (par != 0 && bhi > blo) {
+            const uint64_t c = (edges + par - 1) / par;
+            ch = std::min<uint64_t>(chunk, std::max<uint64_t>(std::min<uint64_t>(kMinChunk, chunk), c));
+        }
+        chunk_len[b] = ch;
+        uint64_t cnt = 0, hubs = 0, slots = 0;
+        for (uint32_t v : rows) {
             uint64_t c = nchunks_of(rp[v + 1] - rp[v], ch);
             cnt += c;
             if (c > 1) { hubs += c; slots += hub_slots(c); }
@@ -96,20 +146,19 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
     std::vector<HubInfo> hub(total ? total : 1);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t b = 0; b < (int64_t)nb; b++) {
-        uint64_t lo, hi;
-        my_range((uint64_t)b, lo, hi);
+        const std::vector<uint32_t>& rows = mine[b];
         Item* it = items.data() + item_ptr[b];
         HubInfo* hb = hub.data() + item_ptr[b];
-        const uint64_t ch = chunk_of_batch(lo, hi);
+        const uint64_t ch = chunk_len[b];
         uint64_t k = 0;
         uint32_t slot = 0;
-        for (uint64_t v = lo; v < hi; v++) {           // hub chunks
+        for (uint32_t v : rows) {                      // hub chunks
             uint64_t deg = rp[v + 1] - rp[v], nc = nchunks_of(deg, ch);
             if (nc <= 1) continue;
             uint64_t base = deg / nc, extra = deg % nc, e0 = rp[v];
             for (uint64_t c = 0; c < nc; c++) {
                 uint32_t len = (uint32_t)(base + (c < extra ? 1 : 0));
-                it[k] = Item{(uint32_t)v, len | kChunkFlag, e0};
+                it[k] = Item{v, len | kChunkFlag, e0};
                 hb[k] = HubInfo{(uint32_t)c, (uint32_t)nc, slot + (uint32_t)c, (uint32_t)deg};
                 e0 += len;
                 k++;
@@ -119,7 +168,7 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
         // remaining rows: counting sort by degree class (0, 1, 2-3, 4-7, ...), descending
         uint64_t cls_cnt[34] = {0};
         auto cls_of = [](uint64_t deg) -> int { return deg == 0 ? 0 : 64 - __builtin_clzll(deg); };
-        for (uint64_t v = lo; v < hi; v++) {
+        for (uint32_t v : rows) {
             uint64_t deg = rp[v + 1] - rp[v];
             if (nchunks_of(deg, ch) > 1) continue;
             cls_cnt[std::min(cls_of(deg), 33)]++;
@@ -127,13 +176,14 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
         uint64_t cls_off[34];
         uint64_t off = k;
         for (int c = 33; c >= 0; c--) { cls_off[c] = off; off += cls_cnt[c]; }
-        for (uint64_t v = lo; v < hi; v++) {
+        for (uint32_t v : rows) {
             uint64_t deg = rp[v + 1] - rp[v];
             if (nchunks_of(deg, ch) > 1) continue;
             uint64_t pos = cls_off[std::min(cls_of(deg), 33)]++;
-            it[pos] = Item{(uint32_t)v, (uint32_t)deg, rp[v]};
+            it[pos] = Item{v, (uint32_t)deg, rp[v]};
             hb[pos] = HubInfo{0, 1, 0, (uint32_t)deg};
         }
+        std::vector<uint32_t>().swap(mine[b]);
     }
     out.nb = nb;
     out.item_ptr.swap(item_ptr);

@@ -132,6 +132,19 @@ class Engine:
         check(lib().f2v_comm_init(self._h, buf, rank, world), "f2v_comm_init")
 
 
+    def comm_peer_export(self):
+        buf = (C.c_char * capi.PEER_BLOB)()
+        check(lib().f2v_comm_peer_export(self._h, buf), "f2v_comm_peer_export")
+        return bytes(buf)
+
+    def comm_peer_init(self, blobs, rank, world):
+        """blobs: the ranks' comm_peer_export() results in rank order."""
+        raw = b"".join(blobs)
+        assert len(raw) == world * capi.PEER_BLOB
+        buf = (C.c_char * len(raw)).from_buffer_copy(raw)
+        check(lib().f2v_comm_peer_init(self._h, buf, rank, world), "f2v_comm_peer_init")
+
+
 class Algorithms:
     """Mirror of the reference's `algorithms` (sample/algorithms.h:51-137), options 5/6/7."""
 

@@ -92,12 +92,12 @@ HUB_DTYPE = np.dtype([("chunk", np.uint32), ("nchunks", np.uint32), ("slot", np.
 CHUNK_FLAG = 0x80000000
 
 
-def plan_build(rowptr, batch, chunk=64, walk=False, rank=0, world=1, first_row=0, nrows=None, par=0):
+def plan_build(rowptr, batch, chunk=64, walk=False, rank=0, world=1, first_row=0, nrows=None, par=0, assign=0):
     """The engine's per-minibatch work plan (f2v_plan_build).  Returns dict of numpy arrays."""
     n = len(rowptr) - 1
     nrows = n - first_row if nrows is None else nrows
     nb, ip, nh, it, hb = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-    check(lib().f2v_plan_build(_p(rowptr), first_row, nrows, batch, chunk, par, int(walk), rank, world,
+    check(lib().f2v_plan_build(_p(rowptr), first_row, nrows, batch, chunk, par, int(walk), rank, world, assign,
                                C.byref(nb), C.byref(ip), C.byref(nh), C.byref(it), C.byref(hb)), "f2v_plan_build")
     nbv = nb.value
     item_ptr = np.ctypeslib.as_array(C.cast(ip, C.POINTER(C.c_uint64)), shape=(nbv + 1,)).copy()

@@ -136,13 +136,29 @@ uint64_t f2v_launch_count(const f2v_engine* e);
 int f2v_last_epoch_ms(f2v_engine* e, float* ms);
 
 /* ---- multi-GPU (one process per GPU) -----------------------------------------------
- * Every rank holds a full replica of X and the CSR.  Each minibatch is split into
- * `world` contiguous slices; a rank updates its slice and the slices are exchanged
+ * Every rank holds a full replica of X and the CSR.  Baseline exchange: each minibatch is
+ * split into `world` contiguous slices; a rank updates its slice and the slices are exchanged
  * with an NCCL all-gather before the next minibatch.  id128: the 128-byte
  * ncclUniqueId produced by f2v_comm_unique_id on rank 0 and broadcast by the caller.
  * batch must be a multiple of world.                                                  */
 int f2v_comm_unique_id(void* id128);
 int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world);
+
+/* Peer-store exchange (the default for N > 1): the exchange is fused into the force kernel.
+ * Every rank maps the other ranks' tables (CUDA IPC between processes, direct peer access
+ * between engines of one process); the kernel stores each finished row into its own replica
+ * AND straight into every peer's replica over NVLink, so the transfer overlaps the compute row
+ * by row; minibatches are separated by one system-scope flag per (rank, step) written by the
+ * last CTA of a launch and polled at the start of the next launch -- no host round trip, no
+ * collective call.  Rows of a minibatch are dealt to the ranks by a degree-balanced greedy
+ * partition (no contiguity needed).  Results equal the single-GPU run bit for bit.
+ *   1. every rank: f2v_comm_peer_export(e, blob)         blob: F2V_PEER_BLOB bytes
+ *   2. the caller all-gathers the blobs in rank order (torch.distributed, MPI, a file ...)
+ *   3. every rank: f2v_comm_peer_init(e, blobs, rank, world)   world <= 8
+ * All ranks must then issue the same sequence of f2v_run_epoch calls.                    */
+#define F2V_PEER_BLOB 256
+int f2v_comm_peer_export(f2v_engine* e, void* blob);
+int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world);
 
 #ifdef __cplusplus
 }

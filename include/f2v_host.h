@@ -60,12 +60,13 @@ int  f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t* n, uint64
  * The plan the engine builds for rows [first_row, first_row+nrows) in minibatches of
  * `batch`: per minibatch, hub rows (degree > chunk; with par > 0 the chunk of a minibatch is
  * clamp(edges/par, 8, chunk)) cut into chunks, then the other rows by
- * descending degree class; with world > 1 only rank's contiguous slice (batch/world rows)
- * of each minibatch.  items: 16-byte records {u32 v; u32 len (bit 31 = hub chunk); u64 e0};
+ * descending degree class; with world > 1 only the rows of each minibatch that `rank` owns:
+ * assign 0 = its contiguous slice of batch/world rows (NCCL all-gather exchange), assign 1 =
+ * degree-balanced greedy partition (peer-store exchange).  items: 16-byte records {u32 v; u32 len (bit 31 = hub chunk); u64 e0};
  * hub: 16-byte records {u32 chunk; u32 nchunks; u32 slot; u32 deg}, parallel to items.
  * All four arrays are malloc'ed (f2v_free).                                                */
 int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64_t nrows, uint32_t batch,
-                   uint32_t chunk, uint32_t par, int walk, int rank, int world, uint64_t* nb,
+                   uint32_t chunk, uint32_t par, int walk, int rank, int world, int assign, uint64_t* nb,
                    uint64_t** item_ptr, uint32_t** n_hub, void** items, void** hub);
 
 /* ---- whole-run driver ------------------------------------------------------------------

@@ -18,7 +18,8 @@ def main():
     rp, ci = host.rmat_csr(13, 16, 2)
     n = len(rp) - 1
     ok = True
-    for model, bs, dim, batch in ((5, 0, 128, 512), (5, 1, 128, 512), (6, 0, 128, 1000), (7, 0, 64, 512), (6, 1, 64, 256)):
+    for model, bs, dim, batch in ((5, 0, 128, 512), (5, 1, 128, 512), (6, 0, 128, 1000), (7, 0, 64, 512), (6, 1, 64, 256),
+                                  (6, 0, 128, 8192), (5, 0, 20, 16)):
         if batch % world:
             batch += world - batch % world
         g = host.RandStream(1)
@@ -39,19 +40,26 @@ def main():
                 eng.run_epoch(model, batch, 5, bs, 0.02)
             return eng.get_embeddings()
 
-        multi = F.Engine(rp, ci, dim, device=local)
-        ids = [F.Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        multi.comm_init(ids[0], rank, world)
-        a = run(multi)
-        multi.close()
         single = F.Engine(rp, ci, dim, device=local)
         b = run(single)
         single.close()
-        same = np.array_equal(a, b)
-        if not same:
-            print("rank", rank, "model", model, "bs", bs, "max diff", np.abs(a - b).max(), flush=True)
-        ok &= same
+        for comm in ("peer", "nccl"):
+            multi = F.Engine(rp, ci, dim, device=local)
+            if comm == "nccl":
+                ids = [F.Engine.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                multi.comm_init(ids[0], rank, world)
+            else:
+                blobs = [None] * world
+                dist.all_gather_object(blobs, multi.comm_peer_export())
+                multi.comm_peer_init(blobs, rank, world)
+            a = run(multi)
+            dist.barrier()           # nobody unmaps a table a peer may still be storing into
+            multi.close()
+            same = np.array_equal(a, b)
+            if not same:
+                print("rank", rank, comm, "model", model, "bs", bs, "max diff", np.abs(a - b).max(), flush=True)
+            ok &= same
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -1,7 +1,7 @@
 """CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- each rank plans only
-its contiguous slice of every minibatch (f2v_plan_build with rank/world, the same code the
-engine uploads), computes that slice, and the slices are all-gathered before the next
-minibatch.  The per-slice compute is stood in for by the oracle so the test runs without a GPU;
+the rows of every minibatch it owns (f2v_plan_build with rank/world, the same code the engine
+uploads: contiguous slices for the NCCL all-gather exchange, the degree-balanced partition for
+the peer-store exchange), computes them, and the rows are exchanged before the next minibatch.  The per-slice compute is stood in for by the oracle so the test runs without a GPU;
 the result must equal the single-rank epoch bit for bit."""
 import os
 import sys
@@ -73,3 +73,66 @@ def test_two_ranks_equal_one_rank(model, bs):
     rp, ci = host.rmat_csr(9, 8, 3)
     want = O.run(model, bs, rp, ci, 16, 1, batch, 5, 0.02)["X"]
     assert np.array_equal(ret["X"], want)
+
+
+def _worker_balanced(rank, world, port, model, batch, ret):
+    """Peer-store exchange protocol: degree-balanced ownership, every rank ends up with every row."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from force2vec_b200 import host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rp, ci = host.rmat_csr(9, 8, 3)
+    n = len(rp) - 1
+    dim, s, lr = 16, 5, 0.02
+    g = host.RandStream(1)
+    X = g.init_embeddings(model, n, dim)
+    walks = g.walks(rp, ci) if model == 7 else None
+    neg = g.epoch_negatives(model, n, batch, s, 0).reshape(-1, s)
+    plan = host.plan_build(rp, batch, 8, walk=(model == 7), rank=rank, world=world, assign=1)
+    deg = np.diff(rp.astype(np.int64))
+    loads = []
+    for b in range(plan["nb"]):
+        items = plan["items"][int(plan["item_ptr"][b]):int(plan["item_ptr"][b + 1])]
+        rows = np.unique(items["v"]).astype(np.int64)
+        lo, hi = b * batch, min(n, (b + 1) * batch)
+        assert rows.size == 0 or (rows.min() >= lo and rows.max() < hi)
+        mine = np.empty((len(rows), dim), np.float32)
+        for k, v in enumerate(rows):                            # Jacobi: every row sees the pre-minibatch table
+            T = X.copy()                                        # (bs=0: one-row steps share the minibatch's negatives)
+            O.step(model, 0, rp, ci, T, int(v), int(v) + 1, neg[b], s, lr, walks=walks)
+            mine[k] = T[v]
+        got = [None] * world
+        dist.all_gather_object(got, (rows, mine))
+        seen = np.concatenate([r for r, _ in got])
+        assert sorted(seen.tolist()) == list(range(lo, hi))     # a partition of the minibatch
+        for r, vals in got:
+            X[r] = vals
+        loads.append([int(deg[r].sum() + 6 * len(r)) for r, _ in got])
+    if rank == 0:
+        ret["X"] = X.copy()
+        ret["loads"] = loads
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model", [5, 6, 7])
+def test_balanced_partition_two_ranks(model):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from force2vec_b200 import host
+    world, batch = 2, 96
+    port = 31500 + (os.getpid() + model * 11) % 2000
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_balanced, args=(world, port, model, batch, ret), nprocs=world, join=True)
+    rp, ci = host.rmat_csr(9, 8, 3)
+    want = O.run(model, 0, rp, ci, 16, 1, batch, 5, 0.02)["X"]
+    assert np.array_equal(ret["X"], want)
+    if model != 7:
+        rp64 = rp.astype(np.int64)
+        for b, l in enumerate(ret["loads"]):                    # greedy LPT: loads differ by at most one row's cost
+            lo, hi = b * batch, min(len(rp) - 1, (b + 1) * batch)
+            biggest = int(np.diff(rp64[lo:hi + 1]).max()) + 6
+            assert abs(l[0] - l[1]) <= biggest, (b, l, biggest)

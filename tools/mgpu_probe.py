@@ -1,0 +1,66 @@
+"""Timing probe for the multi-GPU exchange (run under torch.distributed.run, one rank per GPU).
+Prints per-variant epoch times: full peer-store exchange, without the row stores, without the
+flag barrier, without both (= this rank's share of the compute alone)."""
+import json
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import force2vec_b200 as F  # noqa: E402
+from force2vec_b200 import host  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    scale = int(os.environ.get("SCALE", "20"))
+    model, dim, s = int(os.environ.get("MODEL", "6")), int(os.environ.get("DIM", "128")), 5
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rp, ci = host.rmat_csr(scale, 16, 1)
+    n = len(rp) - 1
+    g = host.RandStream(1)
+    X0 = g.init_embeddings(model, n, dim)
+    eng = F.Engine(rp, ci, dim, device=local)
+    if world > 1:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, eng.comm_peer_export())
+        eng.comm_peer_init(blobs, rank, world)
+    if model != 5:
+        eng.set_lut()
+    eng.set_embeddings(X0)
+    batches = [int(x) for x in os.environ.get("BATCHES", "16384,65536").split(",")]
+    for batch in batches:
+        neg = g.epoch_negatives(model, n, batch, s, 0).copy()
+        eng.set_negatives(neg)
+        # variants with the flag barrier first: once it is off the ranks' step counters run free
+        for dbg, sig, persist in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 0), (1, 1, 0)) + \
+                ((((2, 0, 0), (3, 0, 0), (3, 0, 1))) if batch == batches[-1] else ()):
+            eng.set_option("peer_debug", dbg)
+            eng.set_option("peer_sig", sig)
+            eng.set_option("persist", persist)
+            ms = []
+            for it in range(6):
+                eng.set_negative_offset(0)
+                dist.barrier()
+                torch.cuda.synchronize()
+                eng.run_epoch(model, batch, s, 0, 0.02)
+                ms.append(eng.last_epoch_ms())
+                if dbg & 2:
+                    dist.barrier()
+            t = torch.tensor([min(ms[2:])], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "peer_sig": sig, "persist": persist,
+                                  "ms": float(t.item()),
+                                  "rank0_ms": ms}), flush=True)
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
