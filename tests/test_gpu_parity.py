@@ -334,3 +334,79 @@ def test_full_size_rmat20_properties(oracle):
     for bb in range(nb):
         oracle.step(6, 0, rp, ci, Xo, bb * batch, min(n, (bb + 1) * batch), neg[bb * s:(bb + 1) * s], s, LR, lut=lut_o)
     np.testing.assert_allclose(a, Xo, rtol=1e-4, atol=1e-5)
+
+
+def test_full_size_rmat22_option7(oracle):
+    """BASELINE config 3 at full size (R-MAT scale 22, option 7 semi-random walks, d=64): a whole
+    epoch with the reference's serial libc-stream walks against the oracle, and the device
+    sampler against its host mirror at 21 M draws."""
+    rp, ci = host.rmat_csr(22, 16, 1)
+    n = len(rp) - 1
+    dim, batch, s = 64, 65536, 5
+    g = host.RandStream(1)
+    X0 = g.init_embeddings(7, n, dim)
+    walks = g.walks(rp, ci).copy()
+    neg = g.epoch_negatives(7, n, batch, s, 0).copy()
+    lut = host.build_lut()
+    with F.Engine(rp, ci, dim) as e:
+        e.set_lut(lut)
+        e.set_embeddings(X0)
+        e.set_walks(walks)
+        e.set_negatives(neg)
+        e.run_epoch(7, batch, s, 0, LR)
+        a = e.get_embeddings()
+        e.sample_walks(7, 3)
+        dev = e.get_walks()
+    assert np.array_equal(dev, oracle.walks_counter(7, 3, rp, ci))
+    Xo = X0.copy()
+    nb = (n + batch - 1) // batch
+    lut_o = oracle.build_lut()
+    for bb in range(nb):
+        oracle.step(7, 0, rp, ci, Xo, bb * batch, min(n, (bb + 1) * batch), neg[bb * s:(bb + 1) * s], s, LR,
+                    lut=lut_o, walks=walks)
+    np.testing.assert_allclose(a, Xo, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(os.environ.get("F2V_SKIP_BIG") == "1", reason="F2V_SKIP_BIG=1")
+def test_full_size_rmat24_option5_bs1(oracle):
+    """BASELINE config 4 at full size (R-MAT scale 24: 16.8 M vertices, ~0.5 G CSR entries, option 5
+    with per-vertex negatives, d=128; 2 x 8 GiB tables).  The oracle cannot finish an epoch of this
+    in seconds, so: teacher-forced minibatches (the hub-heavy first one, one from the middle, the
+    last) against the oracle on the full table; a whole epoch twice (bit-reproducible); and the
+    size-independent property that the first minibatch of an epoch equals the teacher-forced step
+    from the same table bit for bit."""
+    scale = int(os.environ.get("F2V_BIG_SCALE", "24"))
+    rp, ci = host.rmat_csr(scale, 16, 1)
+    n = len(rp) - 1
+    dim, batch, s = 128, 65536, 5
+    W = batch + s - 1
+    rng = np.random.default_rng(24)
+    X0 = rng.random((n, dim), dtype=np.float32) * 2.0 - 1.0       # U[-1,1) like randInitF; stream parity is covered elsewhere
+    nb = (n + batch - 1) // batch
+    neg = rng.integers(0, n - 1, size=nb * W, dtype=np.uint32)    # range of randIndex(n-1)
+    with F.Engine(rp, ci, dim) as e:
+        e.set_embeddings(X0)
+        steps = {}
+        for bb in (0, nb // 2, nb - 1):
+            lo, hi = bb * batch, min(n, (bb + 1) * batch)
+            e.step(5, lo, hi - lo, neg[bb * W:bb * W + (hi - lo) + s - 1], s, 1, LR)
+            steps[bb] = e.get_rows(lo, hi - lo)
+            saved = X0[lo:hi].copy()
+            idx = np.zeros(s * batch + s, np.uint32)
+            idx[:(hi - lo) + s - 1] = neg[bb * W:bb * W + (hi - lo) + s - 1]
+            oracle.step(5, 1, rp, ci, X0, lo, hi, idx, s, LR, threads=os.cpu_count() or 1)
+            np.testing.assert_allclose(steps[bb], X0[lo:hi], rtol=1e-4, atol=1e-5)
+            X0[lo:hi] = saved
+            e.set_embeddings(X0)                                  # teacher-forced: back to the same table
+        e.set_negatives(neg)
+        e.run_epoch(5, batch, s, 1, LR)
+        first = e.get_rows(0, batch)
+        probe = [(0, 1 << 18), (n // 2, 1 << 18), (n - (1 << 18), 1 << 18)]
+        a = [e.get_rows(lo, cnt) for lo, cnt in probe]
+        e.set_embeddings(X0)
+        e.set_negatives(neg)
+        e.run_epoch(5, batch, s, 1, LR)
+        b = [e.get_rows(lo, cnt) for lo, cnt in probe]
+    assert np.array_equal(first, steps[0])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y) and np.isfinite(x).all()
