@@ -311,7 +311,8 @@ def run_ours(a):
     # ---- end to end through the host-buffer call
     e2e = None
     if not a.no_e2e:
-        Xin, Xout = X0, torch.empty_like(X0)
+        Xin, Xout = X0, torch.empty(X0.shape, dtype=torch.float32, pin_memory=True)   # empty_like would not pin
+        assert Xin.is_pinned() and Xout.is_pinned()
         base = W + K
 
         def e2e_step(k):

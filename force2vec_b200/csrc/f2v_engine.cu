@@ -109,6 +109,8 @@ struct f2v_engine {
     uint64_t slots_cap = 0;
     Plan epoch_plan, step_plan;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device->host row copies that overlap the epoch (f2v_run_epoch_host)
+    cudaEvent_t ev_rows = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     int epoch_mode = 0;
@@ -131,6 +133,7 @@ struct f2v_engine {
     uint32_t* d_done = nullptr;
     uint64_t step_id = 0;                    // minibatch steps published so far (same on every rank)
     int peer_debug = 0;                      // timing probes only: 1 = no peer row stores, 2 = no flag barrier
+    int pdl = 2;                             // programmatic dependent launch of consecutive minibatches (single GPU)
     int peer_sig = 1;                        // 1: a 1-CTA kernel after the force kernel publishes the step (default);
                                              // 0: the force kernel's last CTA does (a system fence per CTA: measured slower)
 };
@@ -225,6 +228,16 @@ static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
         if (e != cudaSuccess) return e;
         grid = std::min<unsigned>(grid, (unsigned)(sm_count * std::max(per_sm, 1)));
+    }
+    if (p.pdl) {
+        // programmatic dependent launch: may be scheduled while the previous minibatch drains
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWarpsPerCta * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, p);
     }
     kern<<<grid, kWarpsPerCta * 32, smem, st>>>(p);
     return cudaGetLastError();
@@ -330,6 +343,8 @@ int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz, const 
     if (prop.major < 10) { delete e; return fail(F2V_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); }
     CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_rows, cudaEventDisableTiming));
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
     CU(cudaMalloc((void**)&e->d_rowptr, sizeof(uint64_t) * (n + 1)));
@@ -363,6 +378,8 @@ int f2v_destroy(f2v_engine* e) {
     cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_rows) cudaEventDestroy(e->ev_rows);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return F2V_OK;
@@ -533,7 +550,10 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     return F2V_OK;
 }
 
-int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode, float lr, uint32_t chunk) {
+// One epoch.  X_out_host != nullptr (single GPU): finished rows are copied to the host buffer on a
+// second stream while later minibatches still compute (a row is final once its minibatch is done).
+static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode, float lr, uint32_t chunk,
+                          float* X_out_host) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
     if (model == F2V_WALK) bs_mode = 0;
     int r = check_model(e, model, s, bs_mode);
@@ -591,6 +611,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
             k++;
         }
     }
+    uint64_t copy_lo = 0;
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
         p.hub = pl.d_hub + pl.item_ptr[b];
@@ -599,6 +620,7 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
         p.lo = b * batch;
         p.split = b * batch;
         p.neg = e->d_neg + e->neg_off + b * W;
+        p.pdl = (e->pdl && e->world == 1) ? ((b >= 1 && nb >= 2 && e->pdl >= 2) ? 2 : 1) : 0;
         if (e->peer_mode) {
             // minibatch b reads rows its peers stored during step_id (minibatch b-1); it publishes step_id+1
             p.wait_step = (e->peer_debug & 2) ? 0 : e->step_id;
@@ -622,6 +644,17 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
             CU(cudaGetLastError());
             e->launches++;
         }
+        if (X_out_host) {
+            // rows [copy_lo, hi) are final: hand them to the copy stream in pieces of >= 8 MiB
+            const uint64_t hi = std::min<uint64_t>((b + 1) * (uint64_t)batch, e->n);
+            if ((hi - copy_lo) * e->dim * sizeof(float) >= (8u << 20) || b + 1 == nb) {
+                CU(cudaEventRecord(e->ev_rows, e->stream));
+                CU(cudaStreamWaitEvent(e->copy_stream, e->ev_rows, 0));
+                CU(cudaMemcpyAsync(X_out_host + copy_lo * e->dim, Xnew + copy_lo * e->dim,
+                                   sizeof(float) * (hi - copy_lo) * e->dim, cudaMemcpyDeviceToHost, e->copy_stream));
+                copy_lo = hi;
+            }
+        }
         if (e->world > 1 && !e->peer_mode) {
             // exchange the updated slices before the next minibatch reads them
             float* base = Xnew + b * batch * e->dim;
@@ -643,6 +676,10 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
     return F2V_OK;
 }
 
+int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode, float lr, uint32_t chunk) {
+    return run_epoch_impl(e, model, batch, s, bs_mode, lr, chunk, nullptr);
+}
+
 int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode, float lr,
                        uint32_t chunk, const float* X_in, const uint32_t* neg, uint64_t neg_count,
                        const uint32_t* walks, float* X_out) {
@@ -653,11 +690,15 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
         CU(cudaMemcpyAsync(e->d_X[e->cur], X_in, sizeof(float) * e->n * e->dim, cudaMemcpyHostToDevice, e->stream));
     if (neg) { r = f2v_set_negatives(e, neg, neg_count); if (r) return r; }
     if (walks) { r = f2v_set_walks(e, walks); if (r) return r; }
-    r = f2v_run_epoch(e, model, batch, s, bs_mode, lr, chunk);
+    // single GPU: the download is pipelined behind the minibatches; multi-GPU: a replica is complete
+    // only after the epoch's last exchange, so it is copied afterwards
+    const bool overlap = X_out && e->world == 1;
+    r = run_epoch_impl(e, model, batch, s, bs_mode, lr, chunk, overlap ? X_out : nullptr);
     if (r) return r;
-    if (X_out)
+    if (X_out && !overlap)
         CU(cudaMemcpyAsync(X_out, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    if (overlap) CU(cudaStreamSynchronize(e->copy_stream));
     return F2V_OK;
 }
 
@@ -677,6 +718,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "persist")) e->persist = value != 0;
     else if (!strcmp(name, "peer_debug")) e->peer_debug = (int)value;
     else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;
+    else if (!strcmp(name, "pdl")) e->pdl = (int)value;
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }

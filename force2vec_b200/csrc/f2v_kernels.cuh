@@ -75,6 +75,11 @@ struct BatchParams {
     uint64_t signal_step;                // after the last CTA's stores: peers' flags := signal_step
     uint32_t* done;                      // CTA arrival counter of the launch
     uint32_t n_store;                    // peers that receive row stores (= n_peers; 0 only in timing probes)
+    // ---- programmatic dependent launch: this launch may start while its predecessor (the previous
+    // minibatch) is still draining; everything the predecessor can have written is read only after
+    // griddepcontrol.wait.  pdl = 2: the item's own row (from the current table, last written one
+    // epoch ago) is also fetched before the wait.
+    int pdl;
 };
 
 // ------------------------------------------------------------------ PTX helpers --------
@@ -105,6 +110,10 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t byte
 __device__ __forceinline__ void line_prefetch_l2(const void* gmem) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
 }
+// Programmatic dependent launch (sm_90+): wait for the prerequisite grid's completion and memory
+// flush / allow the dependent grid to be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // System-scope flag traffic of the peer-store exchange.
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
     uint64_t v;
@@ -377,7 +386,8 @@ template <class L, int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const uint32_t* __restrict__ idx, uint32_t cnt,
                                              uint32_t self, const BatchParams& p, float sd, int l,
-                                             const float* __restrict__ lut) {
+                                             const float* __restrict__ lut, bool have_first = false,
+                                             uint32_t first = 0) {
     constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
     const float* const Xlo = p.Xlo;
@@ -387,7 +397,7 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     for (uint32_t base = 0; base < cnt_max; base += LPR) {
         const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
         const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
-        const uint32_t mine = (uint32_t)l < nb ? __ldg(idx + base + l) : self;
+        const uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldg(idx + base + l) : self);
         if (L::kBulk && p.prefetch) {
             // the rows of this index block are needed over the next nb/U iterations: start pulling
             // them into L2 now so that later iterations pay L2 latency instead of DRAM latency
@@ -445,15 +455,25 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
     const bool is_chunk = (it.len & kChunkFlag) != 0;
     const uint32_t len = it.len & ~kChunkFlag;
     const uint32_t v = it.v;
+    uint32_t deg = len;
+    HubInfo h{0, 1, 0, 0};
+    if (is_chunk) { h = p.hub[t]; deg = h.deg; }
+    // the item's first block of neighbour ids is static data: fetch it before the dependency wait
+    const uint32_t* const nbr = MODEL == kWalk ? p.walks + (size_t)v * kWalkLen : p.colids + it.e0;
+    const uint32_t nbr_cnt = MODEL == kWalk ? (active ? (uint32_t)kWalkLen : 0u) : len;
+    const bool early_idx = p.pdl != 0 && MODEL != kWalk;     // walks may have been sampled by the predecessor kernel
+    uint32_t first = v;
+    if (early_idx && (uint32_t)l < min((uint32_t)LPR, nbr_cnt)) first = __ldg(nbr + l);
     float xi[NE];
+    if (p.pdl == 1) { pdl_wait(); pdl_launch_dependents(); }
     if (active) L::load_g(xi, ((uint64_t)v < p.split ? p.Xlo : p.Xhi) + (size_t)v * rs, l, p.dim);
     else {
 #pragma unroll
         for (int k = 0; k < NE; k++) xi[k] = 0.f;
     }
-    uint32_t deg = len;
-    HubInfo h{0, 1, 0, 0};
-    if (is_chunk) { h = p.hub[t]; deg = h.deg; }
+    // the dependent launch is released only after this one's own wait: when minibatch b+1 starts,
+    // minibatch b-1 is therefore complete
+    if (p.pdl == 2) { pdl_wait(); pdl_launch_dependents(); }
     float sd = 0.f;
     if (MODEL != kTDist) {
         // degi = 1.0/(deg+1) stored to float (algorithms.cpp:852,1159); STEP*degi in float
@@ -466,10 +486,7 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
 #pragma unroll
     for (int k = 0; k < NE; k++) acc[k] = start_at_xi ? xi[k] : 0.f;
 
-    if (MODEL == kWalk)
-        gather_pairs<L, MODEL, true, LS>(acc, xi, p.walks + (size_t)v * kWalkLen, active ? kWalkLen : 0, v, p, sd, l, lut);
-    else
-        gather_pairs<L, MODEL, true, LS>(acc, xi, p.colids + it.e0, len, v, p, sd, l, lut);
+    gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, sd, l, lut, early_idx, first);
 
     // split rows: publish this chunk's partial sum; the last chunk to arrive folds all of them in
     // chunk order (deterministic) and finishes the row.
@@ -605,6 +622,7 @@ force_batch_kernel(const BatchParams p) {
             const uint32_t lut_bytes = LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u;
             if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes + lut_bytes);
             if (p.wait_step) fence_proxy_async();   // rows written by peers (generic proxy) are read by TMA next
+            if (p.pdl) { pdl_wait(); fence_proxy_async(); }   // negative rows may have been written by the previous minibatch
             __syncwarp();
             if (negs) stage_negatives<L>(p, s_neg, bar);
             if (LS && threadIdx.x == 31) bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, lut_bytes, bar);

@@ -1,0 +1,33 @@
+import sys, os, numpy as np
+sys.path.insert(0, "/root/repo")
+import force2vec_b200 as F
+from force2vec_b200 import host
+from oracle import oracle as O
+bad = 0
+for scale, dim, batches in ((8, 32, (37, 306)), (10, 128, (64, 256, 1000)), (12, 64, (256, 4096))):
+    rp, ci = host.rmat_csr(scale, 4 if scale == 8 else 16, 2)
+    n = len(rp) - 1
+    for model, bs in ((5, 0), (5, 1), (6, 0), (6, 1), (7, 0)):
+        for batch in batches:
+            g = host.RandStream(1)
+            X0 = g.init_embeddings(model, n, dim)
+            st = []
+            for it in range(3):
+                w = g.walks(rp, ci).copy() if model == 7 else None
+                st.append((w, g.epoch_negatives(model, n, batch, 5, bs).copy()))
+            ref = None
+            for pdl in (0, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1):
+                with F.Engine(rp, ci, dim) as e:
+                    e.set_option("pdl", pdl)
+                    e.set_embeddings(X0)
+                    if model != 5: e.set_lut()
+                    for w, neg in st:
+                        if w is not None: e.set_walks(w)
+                        e.set_negatives(neg)
+                        e.run_epoch(model, batch, 5, bs, 0.02)
+                    X = e.get_embeddings()
+                if ref is None: ref = X
+                elif not np.array_equal(ref, X):
+                    bad += 1
+                    print("MISMATCH scale", scale, "model", model, bs, "batch", batch, "pdl", pdl, np.abs(ref - X).max(), flush=True)
+print("stress done, mismatches:", bad)
