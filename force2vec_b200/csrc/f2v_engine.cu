@@ -82,6 +82,8 @@ struct Plan {
     std::vector<uint32_t> n_hub;            // hub-chunk items at the front of each minibatch
     Item* d_items = nullptr;
     HubInfo* d_hub = nullptr;
+    uint64_t* d_item_ptr = nullptr;         // nb+1 offsets (persistent epoch kernel)
+    uint64_t cap_ptr = 0;
     uint64_t cap_items = 0;
     uint32_t max_slots = 0;
 };
@@ -93,7 +95,8 @@ struct f2v_engine {
     std::vector<uint64_t> h_rowptr;          // host copy: the plan is built from degrees
     uint64_t* d_rowptr = nullptr;
     uint32_t* d_colids = nullptr;
-    float* d_X[2] = {nullptr, nullptr};      // ping-pong tables; cur holds the live embedding
+    float* d_Xall = nullptr;                 // one allocation: table 0 then table 1 (rows_alloc rows each)
+    float* d_X[2] = {nullptr, nullptr};      // ping-pong tables inside d_Xall; cur holds the live embedding
     int cur = 0;
     uint64_t rows_alloc = 0;                 // rows allocated per table (n padded for all-gather)
     float* d_lut = nullptr;
@@ -131,6 +134,7 @@ struct f2v_engine {
     bool peer_ipc[kMaxWorld] = {};           // mapping opened with cudaIpcOpenMemHandle
     uint64_t* d_flags = nullptr;             // local flag page, kMaxWorld * kFlagStride u64
     uint32_t* d_done = nullptr;
+    uint32_t* d_bar = nullptr;               // grid-barrier counter of the persistent epoch kernel
     uint64_t step_id = 0;                    // minibatch steps published so far (same on every rank)
     int peer_debug = 0;                      // timing probes only: 1 = no peer row stores, 2 = no flag barrier
     int pdl = 2;                             // programmatic dependent launch of consecutive minibatches (single GPU)
@@ -144,8 +148,9 @@ struct PeerBlob {
     int32_t device;
     uint64_t pid;
     uint64_t n, dim, cur;
-    uint64_t ptr[3];                         // X[0], X[1], flags (valid inside process `pid`)
-    cudaIpcMemHandle_t h[3];
+    uint64_t rows_alloc;
+    uint64_t ptr[2];                         // tables (X[0] then X[1]), flags (valid inside process `pid`)
+    cudaIpcMemHandle_t h[2];
 };
 static_assert(sizeof(PeerBlob) <= F2V_PEER_BLOB, "PeerBlob must fit the ABI's blob size");
 constexpr uint32_t kPeerMagic = 0x46325650u;
@@ -157,6 +162,25 @@ static int ensure(void** p, uint64_t* cap, uint64_t need_bytes) {
     *cap = 0;
     CU(cudaMalloc(p, need_bytes ? need_bytes : 16));
     *cap = need_bytes;
+    return F2V_OK;
+}
+
+// Both tables in one allocation (combined-row addressing in the kernels).  Keeps the live table's
+// first e->n rows when reallocating for a larger row count.
+static int alloc_tables(f2v_engine* e, uint64_t rows) {
+    if (2 * rows > 0xffffffffull) return fail(F2V_ERR_ARG, "table of %llu rows is too large for 32-bit combined row ids", (unsigned long long)rows);
+    float* all = nullptr;
+    const size_t tbl = sizeof(float) * rows * e->dim;
+    CU(cudaMalloc((void**)&all, 2 * tbl));
+    CU(cudaMemset(all, 0, 2 * tbl));
+    if (e->d_Xall) {
+        CU(cudaMemcpy(all + (size_t)e->cur * rows * e->dim, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToDevice));
+        CU(cudaFree(e->d_Xall));
+    }
+    e->d_Xall = all;
+    e->d_X[0] = all;
+    e->d_X[1] = all + rows * e->dim;
+    e->rows_alloc = rows;
     return F2V_OK;
 }
 
@@ -189,6 +213,13 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         CU(cudaMemcpy(pl.d_items, items.data(), sizeof(Item) * total, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(pl.d_hub, hub.data(), sizeof(HubInfo) * total, cudaMemcpyHostToDevice));
     }
+    if (pl.cap_ptr < nb + 1 || !pl.d_item_ptr) {
+        if (pl.d_item_ptr) CU(cudaFree(pl.d_item_ptr));
+        pl.d_item_ptr = nullptr; pl.cap_ptr = 0;
+        CU(cudaMalloc((void**)&pl.d_item_ptr, sizeof(uint64_t) * (nb + 1)));
+        pl.cap_ptr = nb + 1;
+    }
+    CU(cudaMemcpy(pl.d_item_ptr, item_ptr.data(), sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice));
     if (max_slots > e->slots_cap || !e->d_partials) {
         if (e->d_partials) CU(cudaFree(e->d_partials));
         if (e->d_counters) CU(cudaFree(e->d_counters));
@@ -283,6 +314,56 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
     return launch_batch_m<GenL<32>>(model, p, st, sm_count, persist);
 }
 
+// ---- persistent epoch kernel (epoch mode 1): cooperative launch, grid = SMs x resident CTAs
+template <class L, int MODEL>
+static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid_out, bool query) {
+    auto kern = force_epoch_kernel<L, MODEL>;
+    const BatchParams& p = ep.p;
+    const bool negs = L::kBulk && p.neg_in_smem;
+    const bool lut_s = MODEL != kTDist && L::kBulk;
+    const size_t smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0) + (lut_s ? kLutAlloc * sizeof(float) : 0);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const unsigned grid = (unsigned)(sm_count * per_sm);
+    *grid_out = grid;
+    if (query) return cudaSuccess;
+    void* args[] = {(void*)&ep};
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kWarpsPerCta * 32), args, smem, st);
+}
+
+template <class L>
+static cudaError_t launch_epoch_m(int model, const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid, bool query) {
+    switch (model) {
+    case kTDist: return launch_epoch_k<L, kTDist>(ep, st, sm_count, grid, query);
+    case kSigmoid: return launch_epoch_k<L, kSigmoid>(ep, st, sm_count, grid, query);
+    default: return launch_epoch_k<L, kWalk>(ep, st, sm_count, grid, query);
+    }
+}
+
+static cudaError_t launch_epoch(int model, const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid, bool query) {
+    const uint32_t dim = ep.p.dim;
+    switch (dim) {
+    case 32: return launch_epoch_m<VecL<32, 8, 8>>(model, ep, st, sm_count, grid, query);
+    case 64: return launch_epoch_m<VecL<64, 8, 4>>(model, ep, st, sm_count, grid, query);
+    case 128: return launch_epoch_m<VecL<128, 16, 2, 4>>(model, ep, st, sm_count, grid, query);
+    case 256: return launch_epoch_m<VecL<256, 32, 4>>(model, ep, st, sm_count, grid, query);
+    default: break;
+    }
+    if (dim <= 32) return launch_epoch_m<GenL<1>>(model, ep, st, sm_count, grid, query);
+    if (dim <= 64) return launch_epoch_m<GenL<2>>(model, ep, st, sm_count, grid, query);
+    if (dim <= 128) return launch_epoch_m<GenL<4>>(model, ep, st, sm_count, grid, query);
+    if (dim <= 256) return launch_epoch_m<GenL<8>>(model, ep, st, sm_count, grid, query);
+    if (dim <= 512) return launch_epoch_m<GenL<16>>(model, ep, st, sm_count, grid, query);
+    return launch_epoch_m<GenL<32>>(model, ep, st, sm_count, grid, query);
+}
+
 static bool bulk_ok(const f2v_engine* e, uint32_t s, int bs_mode) {
     if (bs_mode != 0 || s == 0 || !e->neg_smem) return false;
     if (!(e->dim == 32 || e->dim == 64 || e->dim == 128 || e->dim == 256)) return false;
@@ -351,9 +432,7 @@ int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz, const 
     CU(cudaMalloc((void**)&e->d_colids, sizeof(uint32_t) * (nnz ? nnz : 1)));
     CU(cudaMemcpy(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice));
     if (nnz) CU(cudaMemcpy(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
-    e->rows_alloc = n;
-    CU(cudaMalloc((void**)&e->d_X[0], sizeof(float) * n * dim));
-    CU(cudaMemset(e->d_X[0], 0, sizeof(float) * n * dim));
+    { int r = alloc_tables(e, n); if (r) { f2v_destroy(e); return r; } }
     CU(cudaMalloc((void**)&e->d_lut, sizeof(float) * kLutAlloc));
     *out = e;
     return F2V_OK;
@@ -367,15 +446,15 @@ int f2v_destroy(f2v_engine* e) {
     for (int r = 0; r < kMaxWorld; r++) {
         if (!e->peer_ipc[r]) continue;
         cudaIpcCloseMemHandle(e->peerX[r][0]);
-        cudaIpcCloseMemHandle(e->peerX[r][1]);
         cudaIpcCloseMemHandle(e->peer_flags[r]);
     }
     cudaFree(e->d_flags); cudaFree(e->d_done);
-    cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_X[0]); cudaFree(e->d_X[1]);
+    cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_Xall);
     cudaFree(e->d_lut); cudaFree(e->d_neg); cudaFree(e->d_walks); cudaFree(e->d_stage);
     cudaFree(e->d_partials); cudaFree(e->d_counters);
-    cudaFree(e->epoch_plan.d_items); cudaFree(e->epoch_plan.d_hub);
-    cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub);
+    cudaFree(e->epoch_plan.d_items); cudaFree(e->epoch_plan.d_hub); cudaFree(e->epoch_plan.d_item_ptr);
+    cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub); cudaFree(e->step_plan.d_item_ptr);
+    cudaFree(e->d_bar);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_rows) cudaEventDestroy(e->ev_rows);
@@ -535,7 +614,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     p.items = e->step_plan.d_items; p.hub = e->step_plan.d_hub;
     p.n_items = (uint32_t)e->step_plan.item_ptr[1]; p.n_hub = e->step_plan.n_hub[0];
     p.lo = first_row; p.split = 0;
-    p.Xlo = e->d_X[e->cur]; p.Xhi = e->d_X[e->cur];
+    p.Xb = e->d_Xall; p.off_lo = p.off_hi = (uint32_t)((uint64_t)e->cur * e->rows_alloc);
     p.out = e->d_stage; p.out_base = first_row;
     p.colids = e->d_colids; p.neg = e->d_neg; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
@@ -572,18 +651,8 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     const uint64_t rows_needed = (e->world > 1 && !e->peer_mode) ? nb * batch : e->n;
     if (e->rows_alloc < rows_needed) {
         CU(cudaStreamSynchronize(e->stream));
-        float* nx = nullptr;
-        CU(cudaMalloc((void**)&nx, sizeof(float) * rows_needed * e->dim));
-        CU(cudaMemset(nx, 0, sizeof(float) * rows_needed * e->dim));
-        CU(cudaMemcpy(nx, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToDevice));
-        CU(cudaFree(e->d_X[e->cur]));
-        e->d_X[e->cur] = nx;
-        if (e->d_X[1 - e->cur]) { CU(cudaFree(e->d_X[1 - e->cur])); e->d_X[1 - e->cur] = nullptr; }
-        e->rows_alloc = rows_needed;
-    }
-    if (!e->d_X[1 - e->cur]) {
-        CU(cudaMalloc((void**)&e->d_X[1 - e->cur], sizeof(float) * e->rows_alloc * e->dim));
-        CU(cudaMemsetAsync(e->d_X[1 - e->cur], 0, sizeof(float) * e->rows_alloc * e->dim, e->stream));
+        r = alloc_tables(e, rows_needed);
+        if (r) return r;
     }
     r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world,
                    e->peer_mode ? kAssignBalanced : kAssignSlices);
@@ -593,7 +662,10 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     float* Xnew = e->d_X[1 - e->cur];
     CU(cudaEventRecord(e->ev0, e->stream));
     BatchParams p{};
-    p.Xlo = Xnew; p.Xhi = Xold; p.out = Xnew; p.out_base = 0;
+    p.Xb = e->d_Xall; p.out = Xnew; p.out_base = 0;
+    p.off_lo = (uint32_t)((uint64_t)(1 - e->cur) * e->rows_alloc);      // rows already updated this epoch: next table
+    p.off_hi = (uint32_t)((uint64_t)e->cur * e->rows_alloc);            // the others: current table
+    (void)Xold;
     p.colids = e->d_colids; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
@@ -611,6 +683,31 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
             k++;
         }
     }
+    if (e->epoch_mode == 1 && nb >= 1 && !(e->world > 1 && !e->peer_mode)) {
+        // one persistent cooperative launch for the whole epoch
+        EpochParams ep{};
+        ep.p = p;
+        ep.p.items = pl.d_items; ep.p.hub = pl.d_hub; ep.p.neg = e->d_neg + e->neg_off;
+        ep.p.pdl = 0; ep.p.wait_step = 0; ep.p.signal_step = 0;
+        ep.item_ptr = pl.d_item_ptr; ep.nb = (uint32_t)nb; ep.batch = batch; ep.neg_stride = (uint32_t)W;
+        ep.step0 = e->step_id;
+        unsigned grid = 0;
+        CU(launch_epoch(model, ep, e->stream, e->sm_count, &grid, true));
+        if ((uint64_t)grid * nb < 0xffffffffull) {
+            if (!e->d_bar) CU(cudaMalloc((void**)&e->d_bar, 128));
+            CU(cudaMemsetAsync(e->d_bar, 0, 128, e->stream));
+            ep.bar_count = e->d_bar;
+            CU(launch_epoch(model, ep, e->stream, e->sm_count, &grid, false));
+            e->launches++;
+            if (e->peer_mode) e->step_id += nb;
+            if (X_out_host)
+                CU(cudaMemcpyAsync(X_out_host, Xnew, sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaEventRecord(e->ev1, e->stream));
+            e->ev_valid = true;
+            e->cur = 1 - e->cur;
+            return F2V_OK;
+        }
+    }
     uint64_t copy_lo = 0;
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
@@ -618,7 +715,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         p.n_items = (uint32_t)(pl.item_ptr[b + 1] - pl.item_ptr[b]);
         p.n_hub = pl.n_hub[b];
         p.lo = b * batch;
-        p.split = b * batch;
+        p.split = (uint32_t)(b * batch);
         p.neg = e->d_neg + e->neg_off + b * W;
         p.pdl = (e->pdl && e->world == 1) ? ((b >= 1 && nb >= 2 && e->pdl >= 2) ? 2 : 1) : 0;
         if (e->peer_mode) {
@@ -704,7 +801,7 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
 
 int f2v_set_epoch_mode(f2v_engine* e, int mode) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
-    if (mode != 0) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
+    if (mode != 0 && mode != 1) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
     e->epoch_mode = mode;
     return F2V_OK;
 }
@@ -764,10 +861,6 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
     if (e->world > 1) return fail(F2V_ERR_STATE, "communicator already initialised");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    if (!e->d_X[1 - e->cur]) {
-        CU(cudaMalloc((void**)&e->d_X[1 - e->cur], sizeof(float) * e->rows_alloc * e->dim));
-        CU(cudaMemset(e->d_X[1 - e->cur], 0, sizeof(float) * e->rows_alloc * e->dim));
-    }
     if (!e->d_flags) {
         CU(cudaMalloc((void**)&e->d_flags, sizeof(uint64_t) * kMaxWorld * kFlagStride));
         CU(cudaMemset(e->d_flags, 0, sizeof(uint64_t) * kMaxWorld * kFlagStride));
@@ -778,8 +871,9 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
     memset(&b, 0, sizeof(b));
     b.magic = kPeerMagic; b.device = e->device; b.pid = (uint64_t)getpid();
     b.n = e->n; b.dim = e->dim; b.cur = (uint64_t)e->cur;
-    void* ptrs[3] = {e->d_X[0], e->d_X[1], e->d_flags};
-    for (int k = 0; k < 3; k++) {
+    b.rows_alloc = e->rows_alloc;
+    void* ptrs[2] = {e->d_Xall, e->d_flags};
+    for (int k = 0; k < 2; k++) {
         b.ptr[k] = (uint64_t)(uintptr_t)ptrs[k];
         CU(cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
     }
@@ -800,10 +894,10 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
         PeerBlob b;
         memcpy(&b, (const char*)blobs + (size_t)r * F2V_PEER_BLOB, sizeof(b));
         if (b.magic != kPeerMagic) return fail(F2V_ERR_ARG, "blob %d is not a peer blob", r);
-        if (b.n != e->n || b.dim != e->dim) return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
+        if (b.n != e->n || b.dim != e->dim || b.rows_alloc != e->rows_alloc) return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
         if (b.cur != (uint64_t)e->cur) return fail(F2V_ERR_STATE, "rank %d is at a different table parity", r);
         if (r == rank) {
-            if (b.ptr[0] != (uint64_t)(uintptr_t)e->d_X[0]) return fail(F2V_ERR_ARG, "blob %d is not this engine's", r);
+            if (b.ptr[0] != (uint64_t)(uintptr_t)e->d_Xall) return fail(F2V_ERR_ARG, "blob %d is not this engine's", r);
             continue;
         }
         if (b.pid == me) {
@@ -816,16 +910,15 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
                 return fail(F2V_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
             cudaGetLastError();
             e->peerX[r][0] = (float*)(uintptr_t)b.ptr[0];
-            e->peerX[r][1] = (float*)(uintptr_t)b.ptr[1];
-            e->peer_flags[r] = (uint64_t*)(uintptr_t)b.ptr[2];
+            e->peer_flags[r] = (uint64_t*)(uintptr_t)b.ptr[1];
         } else {
-            void* m[3] = {nullptr, nullptr, nullptr};
-            for (int k = 0; k < 3; k++) CU(cudaIpcOpenMemHandle(&m[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
+            void* m[2] = {nullptr, nullptr};
+            for (int k = 0; k < 2; k++) CU(cudaIpcOpenMemHandle(&m[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
             e->peerX[r][0] = (float*)m[0];
-            e->peerX[r][1] = (float*)m[1];
-            e->peer_flags[r] = (uint64_t*)m[2];
+            e->peer_flags[r] = (uint64_t*)m[1];
             e->peer_ipc[r] = true;
         }
+        e->peerX[r][1] = e->peerX[r][0] + e->rows_alloc * e->dim;
     }
     e->rank = rank;
     e->world = world;

@@ -46,9 +46,13 @@ struct BatchParams {
     uint32_t n_items;
     uint32_t n_hub;
     uint64_t lo;          // first row of the minibatch (bs=1 window origin)
-    uint64_t split;       // rows < split are read from Xlo, others from Xhi
-    const float* Xlo;
-    const float* Xhi;
+    // Both embedding tables live in ONE allocation (Xb); vertex j is read from row
+    // j + (j < split ? off_lo : off_hi) of it, so a gathered row costs one 32-bit select on the
+    // index (done once per index block, lane-parallel) and one IMAD.WIDE instead of a 64-bit
+    // compare + pointer select per row.  Epoch: off_lo = next table, off_hi = current table.
+    uint32_t split;
+    uint32_t off_lo, off_hi;
+    const float* Xb;
     float* out;
     uint64_t out_base;    // out row of vertex v = out + (v - out_base) * dim
     const uint32_t* colids;
@@ -71,7 +75,7 @@ struct BatchParams {
     float* peer_out[kMaxWorld - 1];      // the peers' copies of `out` (same row indexing)
     uint64_t* peer_flag[kMaxWorld - 1];  // this rank's flag slot in each peer's flag page
     const uint64_t* flags;               // local flag page: flags[r * kFlagStride] written by rank r
-    uint64_t wait_step;                  // before reading Xlo: every peer's flag >= wait_step (0 = no wait)
+    uint64_t wait_step;                  // before reading the next table: every peer's flag >= wait_step (0 = no wait)
     uint64_t signal_step;                // after the last CTA's stores: peers' flags := signal_step
     uint32_t* done;                      // CTA arrival counter of the launch
     uint32_t n_store;                    // peers that receive row stores (= n_peers; 0 only in timing probes)
@@ -80,6 +84,32 @@ struct BatchParams {
     // griddepcontrol.wait.  pdl = 2: the item's own row (from the current table, last written one
     // epoch ago) is also fetched before the wait.
     int pdl;
+};
+
+// What changes from one minibatch to the next (the rest of BatchParams is constant over an epoch).
+struct BatchVar {
+    const Item* items;
+    const HubInfo* hub;
+    uint32_t n_items;
+    uint32_t split;
+    uint32_t lo;
+    const uint32_t* neg;
+};
+__device__ __forceinline__ BatchVar batch_var(const BatchParams& p) {
+    return BatchVar{p.items, p.hub, p.n_items, p.split, (uint32_t)p.lo, p.neg};
+}
+
+// One persistent launch per epoch (f2v_set_epoch_mode 1): every CTA loops over the minibatches,
+// separated by a grid barrier.  p.items / p.hub / p.neg are the bases of the epoch's plan and
+// negative stream.
+struct EpochParams {
+    BatchParams p;
+    const uint64_t* item_ptr;   // nb + 1 offsets into items / hub (device)
+    uint32_t nb;
+    uint32_t batch;
+    uint32_t neg_stride;        // negative indices per minibatch
+    uint32_t* bar_count;        // grid-barrier arrival counter, zeroed before the launch
+    uint64_t step0;             // multi-GPU: exchange step published before this epoch's first minibatch
 };
 
 // ------------------------------------------------------------------ PTX helpers --------
@@ -385,23 +415,23 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_s
 template <class L, int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const uint32_t* __restrict__ idx, uint32_t cnt,
-                                             uint32_t self, const BatchParams& p, float sd, int l,
+                                             uint32_t self, const BatchParams& p, uint32_t split, float sd, int l,
                                              const float* __restrict__ lut, bool have_first = false,
                                              uint32_t first = 0) {
     constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
-    const float* const Xlo = p.Xlo;
-    const float* const Xhi = p.Xhi;
-    const uint64_t split = p.split;
+    const float* const Xb = p.Xb;
+    const uint32_t off_lo = p.off_lo, off_hi = p.off_hi;
     const uint32_t cnt_max = L::G > 1 ? warp_max(cnt) : cnt;
     for (uint32_t base = 0; base < cnt_max; base += LPR) {
         const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
         const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
-        const uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldg(idx + base + l) : self);
+        uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldg(idx + base + l) : self);
+        mine += mine < split ? off_lo : off_hi;          // row of the combined table
         if (L::kBulk && p.prefetch) {
             // the rows of this index block are needed over the next nb/U iterations: start pulling
             // them into L2 now so that later iterations pay L2 latency instead of DRAM latency
-            const float* prow = ((uint64_t)mine < split ? Xlo : Xhi) + (size_t)mine * rs;
+            const float* prow = Xb + (size_t)mine * rs;
             if (p.prefetch == 1) {
                 if ((uint32_t)l < nb) bulk_prefetch_l2(prow, (uint32_t)(rs * sizeof(float)));
             } else {
@@ -422,8 +452,7 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
                 const uint32_t slot = t0 + u;
                 const uint32_t j = __shfl_sync(kFull, mine, slot, LPR);
                 valid[u] = slot < nb;
-                const float* src = ((uint64_t)j < split ? Xlo : Xhi) + (size_t)j * rs;
-                L::load_g(rows[u], src, l, p.dim);
+                L::load_g(rows[u], Xb + (size_t)j * rs, l, p.dim);
             }
             if (U % 2 == 0) {
 #pragma unroll
@@ -439,25 +468,50 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     }
 }
 
+// acc = rows[0] + rows[1] + ... + rows[cnt-1] (in that order), CU partial rows in flight.
+template <class L>
+__device__ __forceinline__ void fold_rows(float (&acc)[L::NE], const float* rows, uint32_t cnt, size_t rs,
+                                          int l, uint32_t dim) {
+    constexpr int NE = L::NE, CU = 4;
+#pragma unroll
+    for (int k = 0; k < NE; k++) acc[k] = 0.f;
+    uint32_t c = 0;
+    for (; c + CU <= cnt; c += CU) {
+        float part[CU][NE];
+#pragma unroll
+        for (int u = 0; u < CU; u++) L::load_g(part[u], rows + (size_t)(c + u) * rs, l, dim);
+#pragma unroll
+        for (int u = 0; u < CU; u++)
+#pragma unroll
+            for (int k = 0; k < NE; k++) acc[k] += part[u][k];
+    }
+    for (; c < cnt; c++) {
+        float part[NE];
+        L::load_g(part, rows + (size_t)c * rs, l, dim);
+#pragma unroll
+        for (int k = 0; k < NE; k++) acc[k] += part[k];
+    }
+}
+
 // G work items, one per group: items t_base .. t_base+G-1 (groups past n_items idle).
 // s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
 template <class L, int MODEL, bool LS>
-__device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_base, const float* s_neg,
-                                              uint64_t* neg_bar, uint32_t neg_parity, int lane,
+__device__ __forceinline__ void process_items(const BatchParams& p, const BatchVar& bv, uint32_t t_base,
+                                              const float* s_neg, uint64_t* neg_bar, uint32_t neg_parity, int lane,
                                               const float* __restrict__ lut) {
     constexpr int NE = L::NE, LPR = L::LPR;
     const int g = lane / LPR, l = lane % LPR;
     const size_t rs = L::stride(p.dim);
     const uint32_t t = t_base + g;
-    const bool active = t < p.n_items;
+    const bool active = t < bv.n_items;
     Item it{0, 0, 0};
-    if (active) it = p.items[t];
+    if (active) it = bv.items[t];
     const bool is_chunk = (it.len & kChunkFlag) != 0;
     const uint32_t len = it.len & ~kChunkFlag;
     const uint32_t v = it.v;
     uint32_t deg = len;
     HubInfo h{0, 1, 0, 0};
-    if (is_chunk) { h = p.hub[t]; deg = h.deg; }
+    if (is_chunk) { h = bv.hub[t]; deg = h.deg; }
     // the item's first block of neighbour ids is static data: fetch it before the dependency wait
     const uint32_t* const nbr = MODEL == kWalk ? p.walks + (size_t)v * kWalkLen : p.colids + it.e0;
     const uint32_t nbr_cnt = MODEL == kWalk ? (active ? (uint32_t)kWalkLen : 0u) : len;
@@ -466,7 +520,7 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
     if (early_idx && (uint32_t)l < min((uint32_t)LPR, nbr_cnt)) first = __ldg(nbr + l);
     float xi[NE];
     if (p.pdl == 1) { pdl_wait(); pdl_launch_dependents(); }
-    if (active) L::load_g(xi, ((uint64_t)v < p.split ? p.Xlo : p.Xhi) + (size_t)v * rs, l, p.dim);
+    if (active) L::load_g(xi, p.Xb + (size_t)(v + (v < bv.split ? p.off_lo : p.off_hi)) * rs, l, p.dim);
     else {
 #pragma unroll
         for (int k = 0; k < NE; k++) xi[k] = 0.f;
@@ -486,44 +540,48 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
 #pragma unroll
     for (int k = 0; k < NE; k++) acc[k] = start_at_xi ? xi[k] : 0.f;
 
-    gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, sd, l, lut, early_idx, first);
+    gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, early_idx, first);
 
-    // split rows: publish this chunk's partial sum; the last chunk to arrive folds all of them in
-    // chunk order (deterministic) and finishes the row.
+    // split rows: publish this chunk's partial sum; the last chunk of a fold block (kFoldBlock
+    // consecutive chunks) to arrive folds the block in chunk order and -- rows with more than one
+    // block -- publishes the block sum; the last block to arrive folds the block sums in block
+    // order and finishes the row.  Deterministic (no float atomics), and the fold's critical path
+    // is ~kFoldBlock + nchunks/kFoldBlock partial rows instead of nchunks.
     bool finish = active;
     if (__any_sync(kFull, is_chunk)) {
         const uint32_t slot0 = h.slot - h.chunk;
+        const uint32_t nblk = (h.nchunks + kFoldBlock - 1) / kFoldBlock;
+        const uint32_t blk = h.chunk / kFoldBlock;
+        const uint32_t blk_n = min((uint32_t)kFoldBlock, h.nchunks - blk * kFoldBlock);
         if (is_chunk) L::store_g(p.partials + (size_t)h.slot * rs, acc, l, p.dim);
         __threadfence();
         __syncwarp();
         uint32_t old = 0;
-        if (is_chunk && l == 0) old = atomicAdd(p.counters + slot0, 1u);
+        if (is_chunk && l == 0) old = atomicAdd(p.counters + slot0 + blk, 1u);
         old = __shfl_sync(kFull, old, 0, LPR);
-        const bool last = is_chunk && old == h.nchunks - 1;
-        if (is_chunk) finish = last;
+        bool last = is_chunk && old == blk_n - 1;
         if (last) {
             __threadfence();
-            if (l == 0) p.counters[slot0] = 0;   // every chunk has arrived: re-arm for the next minibatch
-#pragma unroll
-            for (int k = 0; k < NE; k++) acc[k] = 0.f;
-            constexpr int CU = 4;                // partial rows in flight while folding
-            uint32_t c = 0;
-            for (; c + CU <= h.nchunks; c += CU) {
-                float part[CU][NE];
-#pragma unroll
-                for (int u = 0; u < CU; u++) L::load_g(part[u], p.partials + (size_t)(slot0 + c + u) * rs, l, p.dim);
-#pragma unroll
-                for (int u = 0; u < CU; u++)
-#pragma unroll
-                    for (int k = 0; k < NE; k++) acc[k] += part[u][k];
-            }
-            for (; c < h.nchunks; c++) {
-                float part[NE];
-                L::load_g(part, p.partials + (size_t)(slot0 + c) * rs, l, p.dim);
-#pragma unroll
-                for (int k = 0; k < NE; k++) acc[k] += part[k];
-            }
+            if (l == 0) p.counters[slot0 + blk] = 0;     // every chunk of the block has arrived: re-arm
+            fold_rows<L>(acc, p.partials + (size_t)(slot0 + blk * kFoldBlock) * rs, blk_n, rs, l, p.dim);
         }
+        const bool second = last && nblk > 1;
+        if (__any_sync(kFull, second)) {
+            if (second) L::store_g(p.partials + (size_t)(slot0 + h.nchunks + blk) * rs, acc, l, p.dim);
+            __threadfence();
+            __syncwarp();
+            old = 0;
+            if (second && l == 0) old = atomicAdd(p.counters + slot0 + nblk, 1u);
+            old = __shfl_sync(kFull, old, 0, LPR);
+            const bool last2 = second && old == nblk - 1;
+            if (last2) {
+                __threadfence();
+                if (l == 0) p.counters[slot0 + nblk] = 0;
+                fold_rows<L>(acc, p.partials + (size_t)(slot0 + h.nchunks) * rs, nblk, rs, l, p.dim);
+            }
+            if (second) last = last2;
+        }
+        if (is_chunk) finish = last;
     }
 
     // repulsive part: s negatives (algorithms.cpp:614-627, 898-911, 1172-1183)
@@ -542,8 +600,8 @@ __device__ __forceinline__ void process_items(const BatchParams& p, uint32_t t_b
             pair_update<L, MODEL, false, LS>(acc, xi, row, finish, p.lr, sd, lut);
         }
     } else {
-        const uint32_t* nidx = p.neg + ((p.bs_mode && active) ? (size_t)((uint64_t)v - p.lo) : 0);
-        gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, sd, l, lut);
+        const uint32_t* nidx = bv.neg + ((p.bs_mode && active) ? (size_t)(v - bv.lo) : 0);
+        gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, bv.split, sd, l, lut);
     }
     if (finish) {
         if (MODEL == kTDist || is_chunk) {
@@ -587,12 +645,12 @@ __device__ __forceinline__ void peer_signal(const BatchParams& p) {
 // Stage the minibatch's s shared negative rows in shared memory (TMA bulk copies issued by
 // the lanes of warp 0, completion on the CTA's mbarrier whose expected byte count the caller set).
 template <class L>
-__device__ __forceinline__ void stage_negatives(const BatchParams& p, float* s_neg, uint64_t* bar) {
+__device__ __forceinline__ void stage_negatives(const BatchParams& p, const BatchVar& bv, float* s_neg, uint64_t* bar) {
     const size_t rs = L::stride(p.dim);
     const uint32_t row_bytes = (uint32_t)(rs * sizeof(float));
     for (uint32_t q = threadIdx.x; q < p.s; q += 32) {      // called by warp 0 after expect_tx
-        const uint32_t j = __ldg(p.neg + q);
-        const float* src = ((uint64_t)j < p.split ? p.Xlo : p.Xhi) + (size_t)j * rs;
+        const uint32_t j = __ldg(bv.neg + q);
+        const float* src = p.Xb + (size_t)(j + (j < bv.split ? p.off_lo : p.off_hi)) * rs;
         bulk_g2s(s_neg + (size_t)q * rs, src, row_bytes, bar);
     }
 }
@@ -614,6 +672,7 @@ force_batch_kernel(const BatchParams p) {
     float* s_neg = negs ? reinterpret_cast<float*>(smem_raw + 128) : nullptr;
     const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
     const float* lut = p.lut;
+    const BatchVar bv = batch_var(p);
     peer_wait(p);
     if (negs || LS) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -624,7 +683,7 @@ force_batch_kernel(const BatchParams p) {
             if (p.wait_step) fence_proxy_async();   // rows written by peers (generic proxy) are read by TMA next
             if (p.pdl) { pdl_wait(); fence_proxy_async(); }   // negative rows may have been written by the previous minibatch
             __syncwarp();
-            if (negs) stage_negatives<L>(p, s_neg, bar);
+            if (negs) stage_negatives<L>(p, bv, s_neg, bar);
             if (LS && threadIdx.x == 31) bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, lut_bytes, bar);
         }
         if (LS) {
@@ -636,15 +695,107 @@ force_batch_kernel(const BatchParams p) {
     const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (PERSIST) {
         const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
-        for (uint32_t t_base = gw * L::G; t_base < p.n_items; t_base += stride)
-            process_items<L, MODEL, LS>(p, t_base, s_neg, bar, 0, lane, lut);
+        for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
+            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut);
     } else {
         const uint32_t t_base = gw * L::G;
-        if (t_base < p.n_items) process_items<L, MODEL, LS>(p, t_base, s_neg, bar, 0, lane, lut);
+        if (t_base < bv.n_items) process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut);
     }
     // the CTA's shared memory must stay allocated until the bulk copies have landed
     if (negs || LS) mbar_wait(bar, 0);
     peer_signal(p);
+}
+
+// ------------------------------------------------------------------ persistent epoch ---
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier between two minibatches of the persistent epoch kernel: every row stored by this
+// CTA is visible to the whole grid (and, on a multi-GPU engine, performed in the peers' replicas:
+// system-scope fence) before any CTA reads it.  The last CTA to arrive publishes the exchange step
+// to the peers.  `target` = arrivals expected so far (monotone counter, zeroed before the launch).
+__device__ __forceinline__ void grid_barrier(const BatchParams& p, uint32_t* counter, uint32_t target, uint64_t step) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (p.n_peers) __threadfence_system(); else __threadfence();
+        const uint32_t old = atomicAdd(counter, 1u);
+        if (p.n_peers && old == target - 1) {
+            __threadfence_system();
+            for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], step);
+        }
+        while (ld_acquire_gpu_u32(counter) < target) {}
+    }
+    if (p.n_peers && threadIdx.x < p.world && threadIdx.x != p.rank) {
+        const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
+        while (ld_acquire_sys(f) < step) {}
+    }
+    __syncthreads();
+}
+
+// The whole epoch in one cooperative launch: grid = SMs x resident CTAs; per minibatch every warp
+// strides over the item list (longest items first), the CTA re-stages the minibatch's shared
+// negative rows by TMA, and a grid barrier separates consecutive minibatches (Jacobi rule:
+// minibatch b+1 reads rows minibatch b wrote).  The sigmoid table lives in shared memory for the
+// whole epoch.  For small minibatches this replaces a launch + drain per minibatch (~10 us) by a
+// barrier (~1-2 us).
+template <class L, int MODEL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, L::MINB)
+force_epoch_kernel(const EpochParams ep) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const BatchParams& p = ep.p;
+    constexpr bool LS = MODEL != kTDist && L::kBulk;
+    uint64_t* bar_neg = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* bar_lut = bar_neg + 1;
+    const bool negs = L::kBulk && p.neg_in_smem;
+    float* s_neg = negs ? reinterpret_cast<float*>(smem_raw + 128) : nullptr;
+    const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
+    const float* lut = p.lut;
+    if (threadIdx.x == 0) { mbar_init(bar_neg, 1); mbar_init(bar_lut, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (LS) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar_lut, (uint32_t)(kLutAlloc * sizeof(float)));
+            bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, (uint32_t)(kLutAlloc * sizeof(float)), bar_lut);
+        }
+        lut = reinterpret_cast<const float*>(smem_raw + 128 + neg_bytes);
+        mbar_wait(bar_lut, 0);
+    }
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
+    if (p.n_peers && ep.step0) {
+        // rows the peers stored during the previous epoch's last minibatch
+        if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+            const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
+            while (ld_acquire_sys(f) < ep.step0) {}
+        }
+        __syncthreads();
+    }
+    for (uint32_t b = 0; b < ep.nb; b++) {
+        const uint64_t i0 = ep.item_ptr[b], i1 = ep.item_ptr[b + 1];
+        BatchVar bv;
+        bv.items = p.items + i0;
+        bv.hub = p.hub + i0;
+        bv.n_items = (uint32_t)(i1 - i0);
+        bv.split = b * ep.batch;
+        bv.lo = b * ep.batch;
+        bv.neg = p.neg + (size_t)b * ep.neg_stride;
+        if (negs && threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_expect_tx(bar_neg, neg_bytes);
+            fence_proxy_async();        // rows written with generic stores (this GPU or a peer) are read by TMA next
+            __syncwarp();
+            stage_negatives<L>(p, bv, s_neg, bar_neg);
+        }
+        for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
+            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar_neg, b & 1u, lane, lut);
+        // the staged rows must have landed before shared memory is reused / the CTA exits
+        if (negs) mbar_wait(bar_neg, b & 1u);
+        if (b + 1 < ep.nb || p.n_peers)
+            grid_barrier(p, ep.bar_count, (b + 1) * gridDim.x, ep.step0 + b + 1);
+    }
 }
 
 // A launch with no rows on this rank still takes part in the exchange barrier; the epoch ends with

@@ -23,8 +23,15 @@ struct alignas(16) HubInfo {
 
 constexpr uint32_t kMinChunk = 8;
 
-// partial-sum / counter slots a split row needs: one per chunk (the counter is the first one)
-inline uint32_t hub_slots(uint64_t nchunks) { return (uint32_t)nchunks; }
+// Partial sums of a split row are folded in two levels: blocks of kFoldBlock consecutive chunks,
+// then the block sums.
+constexpr uint32_t kFoldBlock = 32;
+// partial-sum / counter slots a split row needs: one per chunk plus one per fold block (counters:
+// one per block, then one for the second level -- always fewer than the partial slots)
+inline uint32_t hub_slots(uint64_t nchunks) {
+    const uint64_t nblk = (nchunks + kFoldBlock - 1) / kFoldBlock;
+    return (uint32_t)(nchunks + (nblk > 1 ? nblk : 1));
+}
 
 struct HostPlan {
     uint64_t nb = 0;

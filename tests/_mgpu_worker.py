@@ -43,8 +43,10 @@ def main():
         single = F.Engine(rp, ci, dim, device=local)
         b = run(single)
         single.close()
-        for comm in ("peer", "nccl"):
+        for comm in ("peer", "peer_persistent", "nccl"):
             multi = F.Engine(rp, ci, dim, device=local)
+            if comm == "peer_persistent":
+                multi.set_epoch_mode(1)          # one cooperative launch per epoch, exchange barrier inside
             if comm == "nccl":
                 ids = [F.Engine.comm_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(ids, src=0)

@@ -161,7 +161,9 @@ def test_mtx_roundtrip(tmp_path, oracle):
 
 
 def _hub_slots(nc):
-    return nc
+    # one partial-sum slot per chunk, plus one per fold block of 32 chunks (two-level fold)
+    nblk = (nc + 31) // 32
+    return nc + (nblk if nblk > 1 else 1)
 
 
 def _check_plan(rp, batch, chunk, world, par=0):

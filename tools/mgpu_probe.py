@@ -33,30 +33,33 @@ def main():
         eng.set_lut()
     eng.set_embeddings(X0)
     batches = [int(x) for x in os.environ.get("BATCHES", "16384,65536").split(",")]
+    chunks = [int(x) for x in os.environ.get("CHUNKS", "0").split(",")]
     for batch in batches:
         neg = g.epoch_negatives(model, n, batch, s, 0).copy()
         eng.set_negatives(neg)
         # variants with the flag barrier first: once it is off the ranks' step counters run free
-        for dbg, sig, persist in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 0), (1, 1, 0)) + \
-                ((((2, 0, 0), (3, 0, 0), (3, 0, 1))) if batch == batches[-1] else ()):
+        variants = [(0, 1, 0, 0, c) for c in chunks] + [(0, 1, 0, 1, c) for c in chunks]
+        if batch == batches[-1] and os.environ.get("FREE", "1") == "1":
+            variants += [(2, 1, 0, 0, 0), (3, 1, 0, 0, 0)]
+        for dbg, sig, persist, mode, chunk in variants:
             eng.set_option("peer_debug", dbg)
             eng.set_option("peer_sig", sig)
             eng.set_option("persist", persist)
+            eng.set_epoch_mode(mode)
             ms = []
             for it in range(6):
                 eng.set_negative_offset(0)
                 dist.barrier()
                 torch.cuda.synchronize()
-                eng.run_epoch(model, batch, s, 0, 0.02)
+                eng.run_epoch(model, batch, s, 0, 0.02, chunk)
                 ms.append(eng.last_epoch_ms())
                 if dbg & 2:
                     dist.barrier()
             t = torch.tensor([min(ms[2:])], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "peer_sig": sig, "persist": persist,
-                                  "ms": float(t.item()),
-                                  "rank0_ms": ms}), flush=True)
+                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "mode": mode, "chunk": chunk,
+                                  "ms": float(t.item()), "rank0_ms": [round(x, 3) for x in ms]}), flush=True)
     dist.barrier()
     eng.close()
     dist.destroy_process_group()
