@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N>1 exchange: peer = stores into the peers' replicas fused into the force kernel; "
                          "nccl = all-gather per minibatch (baseline)")
+    ap.add_argument("--multicast", type=int, default=1, help="peer exchange through NVLink multicast (NVLS) stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra-batches", default="256,4096,16384", help="comma list of additional batch sizes to report")
@@ -279,6 +280,7 @@ def run_ours(a):
         dist.broadcast_object_list(ids, src=0)
         eng.comm_init(ids[0], rank, world)
     elif world > 1:
+        eng.set_option("multicast", a.multicast)
         blobs = [None] * world
         dist.all_gather_object(blobs, eng.comm_peer_export())
         eng.comm_peer_init(blobs, rank, world)

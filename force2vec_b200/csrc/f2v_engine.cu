@@ -5,6 +5,11 @@
 #include "f2v_kernels.cuh"
 #include "f2v_plan.hpp"
 
+#include <cuda.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <time.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -71,6 +76,106 @@ static int nccl_load() {
     } while (0)
 constexpr int kNcclFloat32 = 7;   // ncclFloat32 in nccl.h's ncclDataType_t
 
+// ------------------------------------------------------------------ driver API (VMM / multicast)
+// Resolved through the runtime (cudaGetDriverEntryPoint): no link-time dependency on libcuda.
+struct DrvApi {
+    bool loaded = false;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+    CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+    CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+    CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+    CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+    CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+    CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+};
+static DrvApi g_drv;
+static int drv_load() {
+    if (g_drv.loaded) return F2V_OK;
+    struct { const char* name; void** slot; } tab[] = {
+        {"cuGetErrorString", (void**)&g_drv.GetErrorString}, {"cuDeviceGet", (void**)&g_drv.DeviceGet},
+        {"cuDeviceGetAttribute", (void**)&g_drv.DeviceGetAttribute}, {"cuMulticastCreate", (void**)&g_drv.MulticastCreate},
+        {"cuMulticastAddDevice", (void**)&g_drv.MulticastAddDevice}, {"cuMulticastBindMem", (void**)&g_drv.MulticastBindMem},
+        {"cuMulticastUnbind", (void**)&g_drv.MulticastUnbind}, {"cuMulticastGetGranularity", (void**)&g_drv.MulticastGetGranularity},
+        {"cuMemCreate", (void**)&g_drv.MemCreate}, {"cuMemRelease", (void**)&g_drv.MemRelease},
+        {"cuMemAddressReserve", (void**)&g_drv.MemAddressReserve}, {"cuMemAddressFree", (void**)&g_drv.MemAddressFree},
+        {"cuMemMap", (void**)&g_drv.MemMap}, {"cuMemUnmap", (void**)&g_drv.MemUnmap}, {"cuMemSetAccess", (void**)&g_drv.MemSetAccess},
+        {"cuMemExportToShareableHandle", (void**)&g_drv.MemExportToShareableHandle},
+        {"cuMemImportFromShareableHandle", (void**)&g_drv.MemImportFromShareableHandle},
+        {"cuMemGetAllocationGranularity", (void**)&g_drv.MemGetAllocationGranularity},
+    };
+    for (auto& t : tab) {
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t r = cudaGetDriverEntryPoint(t.name, t.slot, cudaEnableDefault, &q);
+        if (r != cudaSuccess || q != cudaDriverEntryPointSuccess || !*t.slot)
+            return fail(F2V_ERR_CUDA, "driver entry point %s is not available", t.name);
+    }
+    g_drv.loaded = true;
+    return F2V_OK;
+}
+#define DRV(call)                                                                                  \
+    do {                                                                                           \
+        CUresult _r = (call);                                                                      \
+        if (_r != CUDA_SUCCESS) {                                                                  \
+            const char* _s = nullptr;                                                              \
+            if (g_drv.GetErrorString) g_drv.GetErrorString(_r, &_s);                               \
+            return fail(F2V_ERR_CUDA, "%s failed: %s (%s:%d)", #call, _s ? _s : "?", __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+// ---- tiny unix-socket helpers: the multicast object's file descriptor has to travel from rank 0
+// to the other processes (SCM_RIGHTS), and binding needs two all-rank handshakes
+static int sock_send_fd(int sock, int fd) {
+    char byte = 'F';
+    struct iovec io = {&byte, 1};
+    char ctl[CMSG_SPACE(sizeof(int))];
+    memset(ctl, 0, sizeof(ctl));
+    struct msghdr msg;
+    memset(&msg, 0, sizeof(msg));
+    msg.msg_iov = &io; msg.msg_iovlen = 1; msg.msg_control = ctl; msg.msg_controllen = sizeof(ctl);
+    struct cmsghdr* c = CMSG_FIRSTHDR(&msg);
+    c->cmsg_level = SOL_SOCKET; c->cmsg_type = SCM_RIGHTS; c->cmsg_len = CMSG_LEN(sizeof(int));
+    memcpy(CMSG_DATA(c), &fd, sizeof(int));
+    return sendmsg(sock, &msg, 0) == 1 ? 0 : -1;
+}
+static int sock_recv_fd(int sock) {
+    char byte = 0;
+    struct iovec io = {&byte, 1};
+    char ctl[CMSG_SPACE(sizeof(int))];
+    memset(ctl, 0, sizeof(ctl));
+    struct msghdr msg;
+    memset(&msg, 0, sizeof(msg));
+    msg.msg_iov = &io; msg.msg_iovlen = 1; msg.msg_control = ctl; msg.msg_controllen = sizeof(ctl);
+    if (recvmsg(sock, &msg, 0) != 1) return -1;
+    struct cmsghdr* c = CMSG_FIRSTHDR(&msg);
+    if (!c || c->cmsg_type != SCM_RIGHTS) return -1;
+    int fd = -1;
+    memcpy(&fd, CMSG_DATA(c), sizeof(int));
+    return fd;
+}
+static int sock_byte(int sock, bool send_it, char b) {
+    if (send_it) return send(sock, &b, 1, 0) == 1 ? 0 : -1;
+    char got = 0;
+    return (recv(sock, &got, 1, MSG_WAITALL) == 1 && got == b) ? 0 : -1;
+}
+static void sock_addr(struct sockaddr_un* a, socklen_t* len, const char* name) {
+    memset(a, 0, sizeof(*a));
+    a->sun_family = AF_UNIX;
+    const size_t n = strlen(name);
+    memcpy(a->sun_path + 1, name, n);            // abstract namespace: no file system entry
+    *len = (socklen_t)(offsetof(struct sockaddr_un, sun_path) + 1 + n);
+}
+
 // ------------------------------------------------------------------ engine -------------
 struct Plan {
     uint32_t batch = 0, chunk = 0, par = 0;
@@ -136,7 +241,21 @@ struct f2v_engine {
     uint32_t* d_done = nullptr;
     uint32_t* d_bar = nullptr;               // grid-barrier counter of the persistent epoch kernel
     uint64_t step_id = 0;                    // minibatch steps published so far (same on every rank)
+    // NVLink multicast (NVLS) exchange: tables + flag page live in one VMM allocation bound to a
+    // multicast object shared by all ranks; a store through the multicast mapping lands everywhere
+    int want_mc = 1;                         // option "multicast": use NVLS when every rank supports it
+    bool mc_mode = false;
+    CUmemGenericAllocationHandle mc_handle = 0, vmm_handle = 0;
+    CUdeviceptr vmm_uc = 0, vmm_mc = 0;
+    size_t vmm_size = 0;
+    int listen_sock = -1;
+    char sock_name[48] = "";
+    int trace = 0;                           // option "trace": one CUDA event per minibatch of the last epoch
+    std::vector<cudaEvent_t> trace_ev;
+    uint64_t trace_n = 0;
     int peer_debug = 0;                      // timing probes only: 1 = no peer row stores, 2 = no flag barrier
+    int order = -1;                          // item order after the hub chunks: 0 descending degree, 1 light rows first,
+                                             // 2 light rows interleaved; -1 = default (0 on one GPU, 1 on several)
     int pdl = 2;                             // programmatic dependent launch of consecutive minibatches (single GPU)
     int peer_sig = 1;                        // 1: a 1-CTA kernel after the force kernel publishes the step (default);
                                              // 0: the force kernel's last CTA does (a system fence per CTA: measured slower)
@@ -151,6 +270,8 @@ struct PeerBlob {
     uint64_t rows_alloc;
     uint64_t ptr[2];                         // tables (X[0] then X[1]), flags (valid inside process `pid`)
     cudaIpcMemHandle_t h[2];
+    uint32_t mc_ok;                          // this rank can and wants to use NVLink multicast
+    char sock_name[44];                      // abstract unix socket this rank listens on (fd hand-off)
 };
 static_assert(sizeof(PeerBlob) <= F2V_PEER_BLOB, "PeerBlob must fit the ABI's blob size");
 constexpr uint32_t kPeerMagic = 0x46325650u;
@@ -448,6 +569,20 @@ int f2v_destroy(f2v_engine* e) {
         cudaIpcCloseMemHandle(e->peerX[r][0]);
         cudaIpcCloseMemHandle(e->peer_flags[r]);
     }
+    if (e->listen_sock >= 0) close(e->listen_sock);
+    if (e->mc_mode) {
+        // tables and flags live in the VMM allocation: unmap / unbind / release instead of cudaFree
+        CUdevice dev;
+        g_drv.DeviceGet(&dev, e->device);
+        g_drv.MemUnmap(e->vmm_mc, e->vmm_size);
+        g_drv.MemAddressFree(e->vmm_mc, e->vmm_size);
+        g_drv.MulticastUnbind(e->mc_handle, dev, 0, e->vmm_size);
+        g_drv.MemUnmap(e->vmm_uc, e->vmm_size);
+        g_drv.MemAddressFree(e->vmm_uc, e->vmm_size);
+        g_drv.MemRelease(e->vmm_handle);
+        g_drv.MemRelease(e->mc_handle);
+        e->d_Xall = nullptr; e->d_flags = nullptr;
+    }
     cudaFree(e->d_flags); cudaFree(e->d_done);
     cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_Xall);
     cudaFree(e->d_lut); cudaFree(e->d_neg); cudaFree(e->d_walks); cudaFree(e->d_stage);
@@ -458,6 +593,7 @@ int f2v_destroy(f2v_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_rows) cudaEventDestroy(e->ev_rows);
+    for (cudaEvent_t ev : e->trace_ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -641,7 +777,9 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     if (e->world > 1 && !e->peer_mode && batch % e->world)
         return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
     CU(cudaSetDevice(e->device));
-    if (chunk == 0) chunk = 128;
+    // default hub chunk: 128 edges on one GPU; 64 on a multi-GPU engine, where a rank's share of a
+    // minibatch is small enough for the longest item to be the critical path (measured, N=4)
+    if (chunk == 0) chunk = e->world > 1 ? 64 : 128;
     const uint64_t nb = (e->n + batch - 1) / batch;
     const uint64_t W = neg_stride(model, batch, s, bs_mode);
     if (e->neg_count < e->neg_off + nb * W)
@@ -654,8 +792,9 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         r = alloc_tables(e, rows_needed);
         if (r) return r;
     }
+    const int order = e->order >= 0 ? e->order : (e->peer_mode ? 1 : 0);
     r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world,
-                   e->peer_mode ? kAssignBalanced : kAssignSlices);
+                   (e->peer_mode ? kAssignBalanced : kAssignSlices) | (order == 1 ? kOrderLightFirst : 0) | (order == 2 ? kOrderInterleave : 0));
     if (r) return r;
     const Plan& pl = e->epoch_plan;
     float* Xold = e->d_X[e->cur];
@@ -673,10 +812,15 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     const uint64_t slice = batch / (uint64_t)e->world;
     if (e->peer_mode) {
         p.n_peers = (e->peer_debug & 2) ? 0u : (uint32_t)(e->world - 1);
-        p.n_store = (e->peer_debug & 1) ? 0u : (uint32_t)(e->world - 1);
+        p.n_store = ((e->peer_debug & 1) || e->mc_mode) ? 0u : (uint32_t)(e->world - 1);
+        if (e->mc_mode) {
+            // the same offsets inside the multicast mapping: one store reaches every replica
+            p.mc_out = (float*)((char*)e->vmm_mc + ((char*)Xnew - (char*)e->d_Xall));
+            p.mc_flag = (uint64_t*)((char*)e->vmm_mc + ((char*)e->d_flags - (char*)e->d_Xall)) + (size_t)e->rank * kFlagStride;
+        }
         p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
         p.flags = e->d_flags; p.done = e->d_done;
-        for (int r = 0, k = 0; r < e->world; r++) {
+        for (int r = 0, k = 0; r < e->world && !e->mc_mode; r++) {
             if (r == e->rank) continue;
             p.peer_out[k] = e->peerX[r][1 - e->cur];
             p.peer_flag[k] = e->peer_flags[r] + (size_t)e->rank * kFlagStride;
@@ -709,6 +853,11 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         }
     }
     uint64_t copy_lo = 0;
+    if (e->trace) {
+        while (e->trace_ev.size() < nb + 1) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->trace_ev.push_back(ev); }
+        CU(cudaEventRecord(e->trace_ev[0], e->stream));
+        e->trace_n = nb;
+    }
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
         p.hub = pl.d_hub + pl.item_ptr[b];
@@ -741,6 +890,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
             CU(cudaGetLastError());
             e->launches++;
         }
+        if (e->trace) CU(cudaEventRecord(e->trace_ev[b + 1], e->stream));
         if (X_out_host) {
             // rows [copy_lo, hi) are final: hand them to the copy stream in pieces of >= 8 MiB
             const uint64_t hi = std::min<uint64_t>((b + 1) * (uint64_t)batch, e->n);
@@ -816,6 +966,9 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "peer_debug")) e->peer_debug = (int)value;
     else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;
     else if (!strcmp(name, "pdl")) e->pdl = (int)value;
+    else if (!strcmp(name, "order")) e->order = (int)value;
+    else if (!strcmp(name, "multicast")) e->want_mc = value != 0;
+    else if (!strcmp(name, "trace")) e->trace = (int)value;
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }
@@ -828,6 +981,17 @@ int f2v_last_epoch_ms(f2v_engine* e, float* ms) {
     CU(cudaSetDevice(e->device));
     CU(cudaEventSynchronize(e->ev1));
     CU(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return F2V_OK;
+}
+
+int f2v_trace_ms(f2v_engine* e, float* ms, uint32_t cap, uint32_t* count) {
+    if (!e || !ms || !count) return fail(F2V_ERR_ARG, "null argument");
+    if (!e->trace || e->trace_n == 0) return fail(F2V_ERR_STATE, "no traced epoch (f2v_set_option trace 1, epoch mode 0)");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    const uint32_t n = (uint32_t)std::min<uint64_t>(cap, e->trace_n);
+    for (uint32_t b = 0; b < n; b++) CU(cudaEventElapsedTime(ms + b, e->trace_ev[b], e->trace_ev[b + 1]));
+    *count = n;
     return F2V_OK;
 }
 
@@ -877,8 +1041,147 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
         b.ptr[k] = (uint64_t)(uintptr_t)ptrs[k];
         CU(cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
     }
+    // NVLink multicast: can this device do it, and is a hand-off socket up?
+    b.mc_ok = 0;
+    if (e->want_mc && drv_load() == F2V_OK) {
+        CUdevice dev;
+        int mc = 0, posix = 0;
+        if (g_drv.DeviceGet(&dev, e->device) == CUDA_SUCCESS &&
+            g_drv.DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) == CUDA_SUCCESS &&
+            g_drv.DeviceGetAttribute(&posix, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, dev) == CUDA_SUCCESS &&
+            mc && posix) {
+            if (e->listen_sock < 0) {
+                snprintf(e->sock_name, sizeof(e->sock_name), "f2v-%d-%p", (int)getpid(), (void*)e);
+                int s = socket(AF_UNIX, SOCK_STREAM, 0);
+                struct sockaddr_un a;
+                socklen_t alen;
+                sock_addr(&a, &alen, e->sock_name);
+                if (s >= 0 && bind(s, (struct sockaddr*)&a, alen) == 0 && listen(s, kMaxWorld) == 0) e->listen_sock = s;
+                else if (s >= 0) close(s);
+            }
+            if (e->listen_sock >= 0) {
+                b.mc_ok = 1;
+                memcpy(b.sock_name, e->sock_name, std::min(sizeof(b.sock_name) - 1, strlen(e->sock_name)));
+            }
+        }
+    }
     memset(blob, 0, F2V_PEER_BLOB);
     memcpy(blob, &b, sizeof(b));
+    return F2V_OK;
+}
+
+// Move the tables and the flag page into one VMM allocation bound to a multicast object that all
+// ranks share.  Rank 0 creates the object and hands its file descriptor to the others over a
+// unix socket; two handshakes make sure every device is added before anyone binds and everything
+// is bound before anyone stores.
+static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
+    int r = drv_load();
+    if (r) return r;
+    CUdevice dev;
+    DRV(g_drv.DeviceGet(&dev, e->device));
+    const size_t tbl = sizeof(float) * e->rows_alloc * e->dim;
+    const size_t flags_off = (2 * tbl + 255) / 256 * 256;
+    const size_t need = flags_off + sizeof(uint64_t) * kMaxWorld * kFlagStride;
+    CUmulticastObjectProp mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.numDevices = (unsigned)world;
+    mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    mp.size = need;
+    size_t gran = 0;
+    DRV(g_drv.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = e->device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t agran = 0;
+    DRV(g_drv.MemGetAllocationGranularity(&agran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    gran = std::max(gran, agran);
+    const size_t size = (need + gran - 1) / gran * gran;
+    mp.size = size;
+
+    int conns[kMaxWorld];
+    for (int k = 0; k < kMaxWorld; k++) conns[k] = -1;
+    auto close_all = [&]() { for (int k = 0; k < kMaxWorld; k++) if (conns[k] >= 0) { close(conns[k]); conns[k] = -1; } };
+    CUmemGenericAllocationHandle mc = 0;
+    if (rank == 0) {
+        DRV(g_drv.MulticastCreate(&mc, &mp));
+        int fd = -1;
+        DRV(g_drv.MemExportToShareableHandle(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+        for (int k = 1; k < world; k++) {
+            int c = accept(e->listen_sock, nullptr, nullptr);
+            char who = 0;
+            if (c < 0 || recv(c, &who, 1, MSG_WAITALL) != 1 || who < 1 || who >= world || conns[(int)who] >= 0) {
+                if (c >= 0) close(c);
+                close_all();
+                return fail(F2V_ERR_STATE, "multicast hand-off: bad connection");
+            }
+            conns[(int)who] = c;
+        }
+        for (int k = 1; k < world; k++)
+            if (sock_send_fd(conns[k], fd) != 0) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: cannot send the handle"); }
+        close(fd);
+    } else {
+        int c = socket(AF_UNIX, SOCK_STREAM, 0);
+        struct sockaddr_un a;
+        socklen_t alen;
+        sock_addr(&a, &alen, blobs[0].sock_name);
+        bool up = false;
+        for (int tries = 0; tries < 600 && c >= 0; tries++) {
+            if (connect(c, (struct sockaddr*)&a, alen) == 0) { up = true; break; }
+            struct timespec ts = {0, 100 * 1000 * 1000};
+            nanosleep(&ts, nullptr);
+        }
+        if (!up) { if (c >= 0) close(c); return fail(F2V_ERR_STATE, "multicast hand-off: rank 0 is not reachable"); }
+        conns[0] = c;
+        char who = (char)rank;
+        if (send(c, &who, 1, 0) != 1) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: send failed"); }
+        int fd = sock_recv_fd(c);
+        if (fd < 0) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: no handle received"); }
+        CUresult ir = g_drv.MemImportFromShareableHandle(&mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+        close(fd);
+        if (ir != CUDA_SUCCESS) { close_all(); return fail(F2V_ERR_CUDA, "cuMemImportFromShareableHandle failed (%d)", (int)ir); }
+    }
+    // all-rank handshake through rank 0: `tag` from everyone, then `tag+1` back to everyone
+    auto handshake = [&](char tag) -> int {
+        if (rank == 0) {
+            for (int k = 1; k < world; k++) if (sock_byte(conns[k], false, tag)) return -1;
+            for (int k = 1; k < world; k++) if (sock_byte(conns[k], true, (char)(tag + 1))) return -1;
+            return 0;
+        }
+        if (sock_byte(conns[0], true, tag)) return -1;
+        return sock_byte(conns[0], false, (char)(tag + 1));
+    };
+    DRV(g_drv.MulticastAddDevice(mc, dev));
+    if (handshake('A')) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: add-device handshake failed"); }
+    CUmemGenericAllocationHandle mem = 0;
+    DRV(g_drv.MemCreate(&mem, size, &ap, 0));
+    DRV(g_drv.MulticastBindMem(mc, 0, mem, 0, size, 0));
+    CUmemAccessDesc ad;
+    memset(&ad, 0, sizeof(ad));
+    ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = e->device; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CUdeviceptr uc = 0, mcva = 0;
+    DRV(g_drv.MemAddressReserve(&uc, size, gran, 0, 0));
+    DRV(g_drv.MemMap(uc, size, 0, mem, 0));
+    DRV(g_drv.MemSetAccess(uc, size, &ad, 1));
+    DRV(g_drv.MemAddressReserve(&mcva, size, gran, 0, 0));
+    DRV(g_drv.MemMap(mcva, size, 0, mc, 0));
+    DRV(g_drv.MemSetAccess(mcva, size, &ad, 1));
+    // move the live state over (through the unicast mapping) and drop the cudaMalloc'ed tables
+    CU(cudaMemset((void*)uc, 0, size));
+    CU(cudaMemcpy((void*)uc, e->d_Xall, 2 * tbl, cudaMemcpyDeviceToDevice));
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(e->d_Xall));
+    CU(cudaFree(e->d_flags));
+    e->d_Xall = (float*)uc;
+    e->d_X[0] = e->d_Xall;
+    e->d_X[1] = e->d_Xall + e->rows_alloc * e->dim;
+    e->d_flags = (uint64_t*)((char*)uc + flags_off);
+    e->mc_handle = mc; e->vmm_handle = mem; e->vmm_uc = uc; e->vmm_mc = mcva; e->vmm_size = size;
+    e->mc_mode = true;
+    if (handshake('C')) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: bind handshake failed"); }
+    close_all();
     return F2V_OK;
 }
 
@@ -890,6 +1193,31 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
     if (!e->d_flags) return fail(F2V_ERR_STATE, "call f2v_comm_peer_export first");
     CU(cudaSetDevice(e->device));
     const uint64_t me = (uint64_t)getpid();
+    // NVLink multicast when every rank can and wants to, and the ranks are separate processes
+    // (the hand-off below blocks, so engines of one process driven by one thread cannot use it)
+    if (world > 1) {
+        PeerBlob all[kMaxWorld];
+        bool mc = true;
+        for (int r = 0; r < world; r++) {
+            memcpy(&all[r], (const char*)blobs + (size_t)r * F2V_PEER_BLOB, sizeof(PeerBlob));
+            if (all[r].magic != kPeerMagic) return fail(F2V_ERR_ARG, "blob %d is not a peer blob", r);
+            if (all[r].n != e->n || all[r].dim != e->dim || all[r].rows_alloc != e->rows_alloc)
+                return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
+            if (all[r].cur != (uint64_t)e->cur) return fail(F2V_ERR_STATE, "rank %d is at a different table parity", r);
+            mc = mc && all[r].mc_ok != 0;
+            for (int q = 0; q < r; q++) mc = mc && all[q].pid != all[r].pid;
+        }
+        if (mc) {
+            int rr = mc_setup(e, all, rank, world);
+            if (rr) return rr;
+            e->rank = rank;
+            e->world = world;
+            e->peer_mode = true;
+            e->step_id = 0;
+            if (e->listen_sock >= 0) { close(e->listen_sock); e->listen_sock = -1; }
+            return F2V_OK;
+        }
+    }
     for (int r = 0; r < world; r++) {
         PeerBlob b;
         memcpy(&b, (const char*)blobs + (size_t)r * F2V_PEER_BLOB, sizeof(b));

@@ -78,7 +78,12 @@ struct BatchParams {
     uint64_t wait_step;                  // before reading the next table: every peer's flag >= wait_step (0 = no wait)
     uint64_t signal_step;                // after the last CTA's stores: peers' flags := signal_step
     uint32_t* done;                      // CTA arrival counter of the launch
-    uint32_t n_store;                    // peers that receive row stores (= n_peers; 0 only in timing probes)
+    uint32_t n_store;                    // peers that receive unicast row stores (0 with multicast, or in timing probes)
+    // NVLink multicast (NVLS): `mc_out` is the multicast mapping of the `out` table -- ONE store
+    // lands in every rank's replica (this one included), replicated by the NVSwitch -- and
+    // `mc_flag` the multicast mapping of this rank's exchange flag.  nullptr = unicast peer stores.
+    float* mc_out;
+    uint64_t* mc_flag;
     // ---- programmatic dependent launch: this launch may start while its predecessor (the previous
     // minibatch) is still draining; everything the predecessor can have written is read only after
     // griddepcontrol.wait.  pdl = 2: the item's own row (from the current table, last written one
@@ -153,6 +158,16 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Multicast stores (the address is a multicast mapping; the switch replicates the write).
+__device__ __forceinline__ void mc_st_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mc_st_f32(float* p, float a) {
+    asm volatile("multimem.st.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void mc_st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -201,6 +216,11 @@ struct VecL {
         for (int k = 0; k < VPL; k++)
             __stcg(reinterpret_cast<float4*>(row) + k * LPR + l,
                    make_float4(f[4 * k + 0], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]));
+    }
+    __device__ static __forceinline__ void store_mc(float* row, const float (&f)[NE], int l, uint32_t) {
+#pragma unroll
+        for (int k = 0; k < VPL; k++)
+            mc_st_v4(row + 4 * (k * LPR + l), f[4 * k + 0], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
     }
     // ---- arithmetic on a lane's fragment: packed fp32x2 (FFMA2 / FMUL2 / FADD2 on sm_100a;
     //      every component is rounded exactly like the scalar op)
@@ -285,6 +305,13 @@ struct GenL {
         for (int k = 0; k < NV; k++) {
             uint32_t e = k * 32 + l;
             if (e < dim) __stcg(row + e, f[k]);
+        }
+    }
+    __device__ static __forceinline__ void store_mc(float* row, const float (&f)[NE], int l, uint32_t dim) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t e = k * 32 + l;
+            if (e < dim) mc_st_f32(row + e, f[k]);
         }
     }
     __device__ static __forceinline__ float dot(const float (&a)[NE], const float (&b)[NE]) {
@@ -609,9 +636,14 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
             for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(xi[k], acc[k]);   // X[i] += delta (:629-639)
         }
         const size_t off = (size_t)((uint64_t)v - p.out_base) * rs;
-        L::store_g(p.out + off, acc, l, p.dim);
-        // multi-GPU: the exchange is fused here -- the row goes straight into every peer's replica
-        for (uint32_t r = 0; r < p.n_store; r++) L::store_g(p.peer_out[r] + off, acc, l, p.dim);
+        // multi-GPU: the exchange is fused here -- the row goes straight into every replica, with one
+        // multicast store (NVLS) or one store per peer
+        if (p.mc_out != nullptr) {
+            L::store_mc(p.mc_out + off, acc, l, p.dim);
+        } else {
+            L::store_g(p.out + off, acc, l, p.dim);
+            for (uint32_t r = 0; r < p.n_store; r++) L::store_g(p.peer_out[r] + off, acc, l, p.dim);
+        }
     }
 }
 
@@ -619,11 +651,17 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
 // published the minibatch step that wrote it.  Threads 0..world-1 poll one flag each.
 __device__ __forceinline__ void peer_wait(const BatchParams& p) {
     if (p.wait_step == 0) return;
-    if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+    // with multicast this rank's own rows also come back through the switch: wait for its flag too
+    if (threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
         const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
         while (ld_acquire_sys(f) < p.wait_step) {}
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void publish_step(const BatchParams& p, uint64_t step) {
+    if (p.mc_flag != nullptr) { mc_st_release_sys(p.mc_flag, step); return; }
+    for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], step);
 }
 
 // Exchange barrier, exit side: the last CTA of the launch to finish its (local and peer) stores
@@ -637,7 +675,7 @@ __device__ __forceinline__ void peer_signal(const BatchParams& p) {
         if (old == gridDim.x - 1) {
             *p.done = 0;                         // re-arm for the next launch (stream-ordered)
             __threadfence_system();
-            for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], p.signal_step);
+            publish_step(p, p.signal_step);
         }
     }
 }
@@ -724,11 +762,11 @@ __device__ __forceinline__ void grid_barrier(const BatchParams& p, uint32_t* cou
         const uint32_t old = atomicAdd(counter, 1u);
         if (p.n_peers && old == target - 1) {
             __threadfence_system();
-            for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], step);
+            publish_step(p, step);
         }
         while (ld_acquire_gpu_u32(counter) < target) {}
     }
-    if (p.n_peers && threadIdx.x < p.world && threadIdx.x != p.rank) {
+    if (p.n_peers && threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
         const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
         while (ld_acquire_sys(f) < step) {}
     }
@@ -768,7 +806,7 @@ force_epoch_kernel(const EpochParams ep) {
     const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
     if (p.n_peers && ep.step0) {
         // rows the peers stored during the previous epoch's last minibatch
-        if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+        if (threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
             const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
             while (ld_acquire_sys(f) < ep.step0) {}
         }

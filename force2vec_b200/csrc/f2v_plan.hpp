@@ -63,6 +63,16 @@ inline void slice_range(uint64_t first_row, uint64_t nrows, uint32_t batch, int 
 //                     peer-store exchange, which has no contiguity requirement.
 // Both are pure functions of (rowptr, batch, world): every rank computes the same partition.
 constexpr int kAssignSlices = 0, kAssignBalanced = 1;
+// Flag OR-ed into `assign`: schedule the lightest rows (degree 0..3) right after the hub chunks
+// instead of last.  On a multi-GPU engine these rows are almost pure peer-store traffic; issuing
+// them early lets the NVLink transfer overlap the heavy rows' compute instead of bursting at the
+// end of the launch.
+constexpr int kOrderLightFirst = 2;
+// Flag OR-ed into `assign`: interleave the light rows (degree 0..3) with the heavier ones, two
+// items at a time (the two lane groups of a warp keep items of similar length), in proportion to
+// their counts.  Light rows are almost pure output traffic; spreading them over the launch keeps
+// the multi-GPU row stores below the NVLink egress rate instead of bursting.
+constexpr int kOrderInterleave = 4;
 constexpr uint64_t kRowCost = 6;      // own row + ~5 negatives per vertex
 
 // Rows of minibatch b owned by `rank`, ascending.  world == 1: the whole minibatch.
@@ -70,7 +80,7 @@ inline void owned_rows(const uint64_t* rp, uint64_t first_row, uint64_t nrows, u
                        int assign, bool walk, uint64_t b, std::vector<uint32_t>& rows) {
     rows.clear();
     const uint64_t blo = first_row + b * batch, bhi = std::min(blo + (uint64_t)batch, first_row + nrows);
-    if (world == 1 || assign == kAssignSlices) {
+    if (world == 1 || (assign & 1) == kAssignSlices) {
         uint64_t lo, hi;
         slice_range(first_row, nrows, batch, rank, world, b, lo, hi);
         rows.reserve(hi - lo);
@@ -182,13 +192,31 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
         }
         uint64_t cls_off[34];
         uint64_t off = k;
-        for (int c = 33; c >= 0; c--) { cls_off[c] = off; off += cls_cnt[c]; }
+        if (assign & kOrderLightFirst)
+            for (int c = 0; c <= 2; c++) { cls_off[c] = off; off += cls_cnt[c]; }
+        for (int c = 33; c >= ((assign & kOrderLightFirst) ? 3 : 0); c--) { cls_off[c] = off; off += cls_cnt[c]; }
         for (uint32_t v : rows) {
             uint64_t deg = rp[v + 1] - rp[v];
             if (nchunks_of(deg, ch) > 1) continue;
             uint64_t pos = cls_off[std::min(cls_of(deg), 33)]++;
             it[pos] = Item{v, (uint32_t)deg, rp[v]};
             hb[pos] = HubInfo{0, 1, 0, (uint32_t)deg};
+        }
+        if ((assign & kOrderInterleave) && !(assign & kOrderLightFirst)) {
+            // it[k .. end) is sorted by descending degree class: heavy part then light part (classes 2,1,0)
+            const uint64_t end = item_ptr[b + 1] - item_ptr[b];
+            const uint64_t nlight = cls_cnt[0] + cls_cnt[1] + cls_cnt[2];
+            const uint64_t nheavy = end - k - nlight;
+            if (nlight && nheavy) {
+                std::vector<Item> tmp(it + k, it + end);
+                uint64_t o = k, hi_i = 0, li = 0;
+                while (hi_i < nheavy || li < nlight) {
+                    for (int q = 0; q < 2 && hi_i < nheavy; q++) it[o++] = tmp[hi_i++];
+                    const uint64_t want = hi_i >= nheavy ? nlight : (hi_i * nlight / nheavy) & ~1ull;
+                    while (li < want) it[o++] = tmp[nheavy + li++];
+                }
+                for (uint64_t q = k; q < end; q++) hb[q] = HubInfo{0, 1, 0, it[q].len};
+            }
         }
         std::vector<uint32_t>().swap(mine[b]);
     }

@@ -120,6 +120,13 @@ class Engine:
         check(lib().f2v_last_epoch_ms(self._h, C.byref(ms)), "f2v_last_epoch_ms")
         return ms.value
 
+    def trace_ms(self, cap=1 << 16):
+        """Per-minibatch device times (ms) of the last epoch; needs set_option("trace", 1)."""
+        buf = np.zeros(cap, np.float32)
+        cnt = C.c_uint32()
+        check(lib().f2v_trace_ms(self._h, _p(buf), cap, C.byref(cnt)), "f2v_trace_ms")
+        return buf[:cnt.value].copy()
+
     # ---- multi-GPU
     @staticmethod
     def comm_unique_id():

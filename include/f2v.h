@@ -109,7 +109,9 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows,
  * ranges in natural order (algorithms.cpp:569-640), consuming the resident negative
  * stream (ceil(n/batch)*W entries) and, for model 7, the resident walks.  Same result
  * as a loop of f2v_step.  Asynchronous on the engine's stream.
- * chunk: hub rows longer than `chunk` edges are split across warps (0 = default).     */
+ * chunk: hub rows longer than `chunk` edges are split across warps (0 = default: 128 on a
+ * single-GPU engine, 64 on a multi-GPU one).  Results are bit-identical across world sizes
+ * and epoch modes for equal `chunk`.                                                   */
 int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode,
                   float lr, uint32_t chunk);
 
@@ -134,6 +136,11 @@ uint64_t f2v_launch_count(const f2v_engine* e);
 /* Device time of the last f2v_run_epoch in milliseconds (CUDA events on its stream);
  * synchronises.                                                                       */
 int f2v_last_epoch_ms(f2v_engine* e, float* ms);
+
+/* Per-minibatch device times of the last f2v_run_epoch (epoch mode 0) when the option "trace"
+ * is 1: ms[b] = time from the end of minibatch b-1 to the end of minibatch b (its exchange
+ * included).  Development / profiling aid.                                               */
+int f2v_trace_ms(f2v_engine* e, float* ms, uint32_t cap, uint32_t* count);
 
 /* ---- multi-GPU (one process per GPU) -----------------------------------------------
  * Every rank holds a full replica of X and the CSR.  Baseline exchange: each minibatch is

@@ -62,7 +62,8 @@ int  f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t* n, uint64
  * clamp(edges/par, 8, chunk)) cut into chunks, then the other rows by
  * descending degree class; with world > 1 only the rows of each minibatch that `rank` owns:
  * assign 0 = its contiguous slice of batch/world rows (NCCL all-gather exchange), assign 1 =
- * degree-balanced greedy partition (peer-store exchange).  items: 16-byte records {u32 v; u32 len (bit 31 = hub chunk); u64 e0};
+ * degree-balanced greedy partition (peer-store exchange); assign | 2 = the lightest rows
+ * (degree 0..3) are scheduled right after the hub chunks instead of last.  items: 16-byte records {u32 v; u32 len (bit 31 = hub chunk); u64 e0};
  * hub: 16-byte records {u32 chunk; u32 nchunks; u32 slot; u32 deg}, parallel to items.
  * All four arrays are malloc'ed (f2v_free).                                                */
 int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64_t nrows, uint32_t batch,

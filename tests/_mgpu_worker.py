@@ -37,16 +37,19 @@ def main():
                 if w is not None:
                     eng.set_walks(w)
                 eng.set_negatives(neg)
-                eng.run_epoch(model, batch, 5, bs, 0.02)
+                eng.run_epoch(model, batch, 5, bs, 0.02, chunk=64)   # same hub chunking on every engine
             return eng.get_embeddings()
 
         single = F.Engine(rp, ci, dim, device=local)
         b = run(single)
         single.close()
-        for comm in ("peer", "peer_persistent", "nccl"):
+        # peer: NVLink multicast stores where the box supports them; peer_unicast: one store per peer
+        for comm in ("peer", "peer_unicast", "peer_persistent", "nccl"):
             multi = F.Engine(rp, ci, dim, device=local)
             if comm == "peer_persistent":
                 multi.set_epoch_mode(1)          # one cooperative launch per epoch, exchange barrier inside
+            if comm == "peer_unicast":
+                multi.set_option("multicast", 0)
             if comm == "nccl":
                 ids = [F.Engine.comm_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(ids, src=0)

@@ -26,6 +26,7 @@ def main():
     X0 = g.init_embeddings(model, n, dim)
     eng = F.Engine(rp, ci, dim, device=local)
     if world > 1:
+        eng.set_option("multicast", int(os.environ.get("MC", "1")))
         blobs = [None] * world
         dist.all_gather_object(blobs, eng.comm_peer_export())
         eng.comm_peer_init(blobs, rank, world)
@@ -38,13 +39,14 @@ def main():
         neg = g.epoch_negatives(model, n, batch, s, 0).copy()
         eng.set_negatives(neg)
         # variants with the flag barrier first: once it is off the ranks' step counters run free
-        variants = [(0, 1, 0, 0, c) for c in chunks] + [(0, 1, 0, 1, c) for c in chunks]
+        orders = [int(x) for x in os.environ.get("ORDERS", "0").split(",")]
+        variants = [(0, 1, o, 0, c) for c in chunks for o in orders]
         if batch == batches[-1] and os.environ.get("FREE", "1") == "1":
-            variants += [(2, 1, 0, 0, 0), (3, 1, 0, 0, 0)]
+            variants += [(2, 1, o, 0, chunks[-1]) for o in orders] + [(3, 1, 0, 0, chunks[-1])]
         for dbg, sig, persist, mode, chunk in variants:
             eng.set_option("peer_debug", dbg)
             eng.set_option("peer_sig", sig)
-            eng.set_option("persist", persist)
+            eng.set_option("order", persist)
             eng.set_epoch_mode(mode)
             ms = []
             for it in range(6):
@@ -55,10 +57,23 @@ def main():
                 ms.append(eng.last_epoch_ms())
                 if dbg & 2:
                     dist.barrier()
+            if os.environ.get("TRACE") == "1":
+                eng.set_option("trace", 1)
+                eng.set_negative_offset(0)
+                dist.barrier()
+                torch.cuda.synchronize()
+                eng.run_epoch(model, batch, s, 0, 0.02, chunk)
+                tr = eng.trace_ms()
+                eng.set_option("trace", 0)
+                allt = [None] * world
+                dist.all_gather_object(allt, [round(float(x) * 1e3, 1) for x in tr])
+                if rank == 0:
+                    for r_, t_ in enumerate(allt):
+                        print(json.dumps({"trace_us_rank": r_, "dbg": dbg, "order": persist, "us": t_}), flush=True)
             t = torch.tensor([min(ms[2:])], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "mode": mode, "chunk": chunk,
+                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "mode": mode, "chunk": chunk, "order": persist,
                                   "ms": float(t.item()), "rank0_ms": [round(x, 3) for x in ms]}), flush=True)
     dist.barrier()
     eng.close()
