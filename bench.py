@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--lr", type=float, default=0.02)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0, help="engine epoch mode (0 per-minibatch launches, 1 persistent)")
-    ap.add_argument("--variant", type=int, default=3, help="d=128 kernel lane layout (f2v_set_option)")
+    ap.add_argument("--variant", type=int, default=-1, help="d=128 kernel lane layout (f2v_set_option; -1 = auto)")
     ap.add_argument("--neg-smem", type=int, default=1)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N>1 exchange: peer = stores into the peers' replicas fused into the force kernel; "

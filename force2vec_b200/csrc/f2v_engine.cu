@@ -222,9 +222,8 @@ struct f2v_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     int epoch_mode = 0;
-    int variant = 3;
+    int variant = -1;                        // d=128 lane layout: -1 auto, see launch_batch
     int neg_smem = 1;
-    int prefetch = 0;
     int persist = 0;                         // 1: persistent CTAs striding over the item list (measured slower)
     int par = 9472;                          // adaptive-chunk target: 148 SMs x 64 lane groups (0 = fixed chunk)
     uint64_t launches = 0;
@@ -414,7 +413,10 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
     case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st, sm_count, persist);
     case 64: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count, persist);
     case 128:
-        switch (p.variant) {
+        // auto (-1): 4 CTAs/SM at 64 registers; launches with many items run 5 CTAs/SM at 48 registers
+        // (a few spilled values, 25 % more gathered rows in flight: measured 5-9 % faster from ~64 K items,
+        // slower below)
+        switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u ? 8 : 3)) {
         case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st, sm_count, persist);
         case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st, sm_count, persist);
         case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count, persist);
@@ -422,6 +424,9 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         case 5: return launch_batch_m<VecL<128, 8, 1, 3>>(model, p, st, sm_count, persist);
         case 6: return launch_batch_m<VecL<128, 16, 4, 2>>(model, p, st, sm_count, persist);
         case 7: return launch_batch_m<VecL<128, 8, 1, 4>>(model, p, st, sm_count, persist);
+        case 8: return launch_batch_m<VecL<128, 16, 2, 5>>(model, p, st, sm_count, persist);
+        case 9: return launch_batch_m<VecL<128, 16, 2, 6>>(model, p, st, sm_count, persist);
+        case 10: return launch_batch_m<VecL<128, 16, 2, 7>>(model, p, st, sm_count, persist);
         default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st, sm_count, persist);   // 3
         }
     case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st, sm_count, persist);
@@ -755,7 +760,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     p.colids = e->d_colids; p.neg = e->d_neg; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
-    p.lr = lr; p.variant = e->variant; p.prefetch = e->prefetch;
+    p.lr = lr; p.variant = e->variant;
     CU(launch_batch(model, p, e->stream, e->sm_count, e->persist));
     e->launches++;
     // apply after the join (algorithms.cpp:629-639 / :913-921)
@@ -808,7 +813,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     p.colids = e->d_colids; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
-    p.lr = lr; p.variant = e->variant; p.prefetch = e->prefetch;
+    p.lr = lr; p.variant = e->variant;
     const uint64_t slice = batch / (uint64_t)e->world;
     if (e->peer_mode) {
         p.n_peers = (e->peer_debug & 2) ? 0u : (uint32_t)(e->world - 1);
@@ -961,7 +966,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     if (!strcmp(name, "variant")) e->variant = (int)value;
     else if (!strcmp(name, "neg_smem")) e->neg_smem = value != 0;
     else if (!strcmp(name, "par")) e->par = (int)value;
-    else if (!strcmp(name, "prefetch")) e->prefetch = (int)value;
+    else if (!strcmp(name, "prefetch")) { (void)value; }   // L2 prefetch variants were measured (no gain) and removed
     else if (!strcmp(name, "persist")) e->persist = value != 0;
     else if (!strcmp(name, "peer_debug")) e->peer_debug = (int)value;
     else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;

@@ -35,7 +35,10 @@ constexpr int kTDist = 5, kSigmoid = 6, kWalk = 7;
 constexpr int kWalkLen = 5;
 constexpr int kLutSize = 2048;
 constexpr int kLutAlloc = 2052;          // padded to a multiple of 16 bytes
-constexpr int kWarpsPerCta = 8;
+#ifndef F2V_WARPS
+#define F2V_WARPS 8
+#endif
+constexpr int kWarpsPerCta = F2V_WARPS;   // warps per CTA (tuning: -DF2V_WARPS=9 caps the kernels at 56 registers)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxWorld = 8;             // ranks of one NVSwitch domain
 constexpr int kFlagStride = 16;          // u64 per exchange flag: one 128-byte line each
@@ -66,7 +69,6 @@ struct BatchParams {
     int bs_mode;
     int neg_in_smem;
     int variant;          // layout variant of the d=128 kernels (tuning knob)
-    int prefetch;         // 0 none, 1 TMA bulk L2 prefetch of a whole index block's rows, 2 per-line L2 prefetch
     float lr;
     // ---- peer-store exchange (multi-GPU): every finished row is also stored into the other
     // ranks' replicas of `out` over NVLink; one flag per (source rank) and minibatch step.
@@ -137,13 +139,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// TMA bulk prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address into L2.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void line_prefetch_l2(const void* gmem) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
 }
 // Programmatic dependent launch (sm_90+): wait for the prerequisite grid's completion and memory
 // flush / allow the dependent grid to be scheduled.
@@ -455,20 +450,6 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
         const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
         uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldg(idx + base + l) : self);
         mine += mine < split ? off_lo : off_hi;          // row of the combined table
-        if (L::kBulk && p.prefetch) {
-            // the rows of this index block are needed over the next nb/U iterations: start pulling
-            // them into L2 now so that later iterations pay L2 latency instead of DRAM latency
-            const float* prow = Xb + (size_t)mine * rs;
-            if (p.prefetch == 1) {
-                if ((uint32_t)l < nb) bulk_prefetch_l2(prow, (uint32_t)(rs * sizeof(float)));
-            } else {
-                if ((uint32_t)l < nb) {
-#pragma unroll
-                    for (uint32_t ln = 0; ln < (uint32_t)(rs * sizeof(float)); ln += 128)
-                        line_prefetch_l2(reinterpret_cast<const char*>(prow) + ln);
-                }
-            }
-        }
         for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
             bool valid[U];

@@ -126,8 +126,10 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
 /* Execution mode of f2v_run_epoch: 0 = one kernel launch per minibatch (default),
  * 1 = one persistent cooperative kernel per epoch with a grid barrier per minibatch.  */
 int f2v_set_epoch_mode(f2v_engine* e, int mode);
-/* Tuning knobs (integers): "variant" = lane layout of the d=128 kernels (3 default: 16 lanes
- * per row, 2 rows in flight per group, 4 CTAs/SM; 0: 16x4; 1: 32x8; 2: 8x2; ...), "neg_smem"
+/* Tuning knobs (integers): "variant" = lane layout of the d=128 kernels (-1 default = auto: 16
+ * lanes per row, 2 rows in flight per group, 4 CTAs/SM at 64 registers, or 5 CTAs/SM at 48
+ * registers for launches with >= 48 K items; 3 / 8 force one of the two; 0: 16x4; 1: 32x8; 2: 8x2;
+ * ...), "neg_smem"
  * = 0 disables the TMA staging of shared negatives (they are then gathered from L2 like bs=1
  * negatives), "par" = lane groups a minibatch should fill (adaptive chunk length, 0 = fixed). */
 int f2v_set_option(f2v_engine* e, const char* name, int64_t value);

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--bs", type=int, default=0)
     ap.add_argument("--batches", default="16384")
-    ap.add_argument("--variants", default="3")
+    ap.add_argument("--variants", default="-1")
     ap.add_argument("--chunks", default="64")
     ap.add_argument("--modes", default="0")
     ap.add_argument("--negsmem", default="1")
