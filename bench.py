@@ -338,9 +338,16 @@ def run_ours(a):
             t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_sec = float(t.item())
+        # bytes over PCIe per step, whole job: with the peer exchange every rank moves 1/world of the
+        # table each way (NCCL mode: every rank moves the whole table)
+        tbl = n * a.dim * 4
+        copies = 1 if (world == 1 or a.comm == "peer") else world
         e2e = {"value": pairs / (e2e_sec / K), "unit": "pairs/s",
-               "h2d_bytes_per_step": int(n * a.dim * 4 + stride * 4), "d2h_bytes_per_step": int(n * a.dim * 4),
-               "ms_per_step": e2e_sec / K * 1e3, "call": "f2v_run_epoch_host (pinned host table in/out)"}
+               "h2d_bytes_per_step": int(tbl * copies + stride * 4 * world), "d2h_bytes_per_step": int(tbl * copies),
+               "ms_per_step": e2e_sec / K * 1e3,
+               "call": "f2v_run_epoch_host (pinned host table in/out" +
+                       ("" if world == 1 else "; each rank moves its 1/%d share over PCIe, the rest over NVLink" % world
+                        if a.comm == "peer" else "; every rank moves the whole table") + ")"}
 
     cs.__exit__()
     clocks = cs.summary()

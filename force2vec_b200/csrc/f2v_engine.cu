@@ -938,8 +938,57 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
     if (!e) return fail(F2V_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     int r;
-    if (X_in)
-        CU(cudaMemcpyAsync(e->d_X[e->cur], X_in, sizeof(float) * e->n * e->dim, cudaMemcpyHostToDevice, e->stream));
+    // multi-GPU with the peer exchange: rank r moves only rows [lo, hi) = its 1/world share of the
+    // table over PCIe, in both directions; the other replicas get them over NVLink
+    const bool sharded = e->peer_mode && e->world > 1;
+    const uint64_t per = (e->n + (uint64_t)e->world - 1) / (uint64_t)e->world;
+    const uint64_t lo = sharded ? std::min<uint64_t>(e->n, (uint64_t)e->rank * per) : 0;
+    const uint64_t hi = sharded ? std::min<uint64_t>(e->n, lo + per) : e->n;
+    if (X_in && hi > lo)
+        CU(cudaMemcpyAsync(e->d_X[e->cur] + lo * e->dim, X_in + lo * e->dim, sizeof(float) * (hi - lo) * e->dim,
+                           cudaMemcpyHostToDevice, e->stream));
+    if (X_in && sharded) {
+        BcastParams b{};
+        const size_t off = (size_t)((e->d_X[e->cur] + lo * e->dim) - e->d_Xall);
+        b.src = e->d_Xall + off;
+        const uint64_t floats = (hi - lo) * e->dim;
+        const bool vec = (off % 4 == 0) && (floats % 4 == 0);
+        b.count = vec ? floats / 4 : floats;
+        if (e->mc_mode) {
+            b.mc = (float*)e->vmm_mc + off;      // also rewrites this rank's own rows with the same values
+        } else {
+            for (int q = 0, k = 0; q < e->world; q++) {
+                if (q == e->rank) continue;
+                b.peer[k++] = e->peerX[q][0] + off;
+            }
+            b.n_store = (uint32_t)(e->world - 1);
+        }
+        if (b.count) {
+            const unsigned grid = (unsigned)std::min<uint64_t>((b.count + 255) / 256, (uint64_t)e->sm_count * 8);
+            if (vec) bcast_rows_kernel<true><<<grid, 256, 0, e->stream>>>(b);
+            else bcast_rows_kernel<false><<<grid, 256, 0, e->stream>>>(b);
+            CU(cudaGetLastError());
+            e->launches++;
+        }
+        // publish: one exchange step; the epoch's first minibatch waits for every rank's rows
+        BatchParams p{};
+        p.n_peers = (uint32_t)(e->world - 1);
+        p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
+        p.flags = e->d_flags; p.done = e->d_done;
+        if (e->mc_mode) {
+            p.mc_flag = (uint64_t*)((char*)e->vmm_mc + ((char*)e->d_flags - (char*)e->d_Xall)) + (size_t)e->rank * kFlagStride;
+        } else {
+            for (int q = 0, k = 0; q < e->world; q++) {
+                if (q == e->rank) continue;
+                p.peer_flag[k++] = e->peer_flags[q] + (size_t)e->rank * kFlagStride;
+            }
+        }
+        p.wait_step = 0;
+        p.signal_step = ++e->step_id;
+        peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
+        CU(cudaGetLastError());
+        e->launches++;
+    }
     if (neg) { r = f2v_set_negatives(e, neg, neg_count); if (r) return r; }
     if (walks) { r = f2v_set_walks(e, walks); if (r) return r; }
     // single GPU: the download is pipelined behind the minibatches; multi-GPU: a replica is complete
@@ -947,8 +996,9 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
     const bool overlap = X_out && e->world == 1;
     r = run_epoch_impl(e, model, batch, s, bs_mode, lr, chunk, overlap ? X_out : nullptr);
     if (r) return r;
-    if (X_out && !overlap)
-        CU(cudaMemcpyAsync(X_out, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
+    if (X_out && !overlap && hi > lo)
+        CU(cudaMemcpyAsync(X_out + lo * e->dim, e->d_X[e->cur] + lo * e->dim, sizeof(float) * (hi - lo) * e->dim,
+                           cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (overlap) CU(cudaStreamSynchronize(e->copy_stream));
     return F2V_OK;

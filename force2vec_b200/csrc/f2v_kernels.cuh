@@ -824,6 +824,32 @@ __global__ void peer_sync_kernel(const BatchParams p) {
     peer_signal(p);
 }
 
+// Replicate a row range of this rank's table into every other replica (multi-GPU host-buffer
+// epoch: each rank uploads 1/world of the table over its own PCIe link and the rest travels over
+// NVLink).  dst of element i: the multicast mapping (one store reaches all) or each peer's table.
+struct BcastParams {
+    const float* src;
+    float* mc;
+    float* peer[kMaxWorld - 1];
+    uint32_t n_store;
+    uint64_t count;                      // float4 elements (VEC) or floats
+};
+template <bool VEC>
+__global__ void bcast_rows_kernel(const BcastParams b) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.count; i += stride) {
+        if (VEC) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(b.src) + i);
+            if (b.mc) mc_st_v4(b.mc + 4 * i, v.x, v.y, v.z, v.w);
+            for (uint32_t r = 0; r < b.n_store; r++) __stcg(reinterpret_cast<float4*>(b.peer[r]) + i, v);
+        } else {
+            const float v = __ldcg(b.src + i);
+            if (b.mc) mc_st_f32(b.mc + i, v);
+            for (uint32_t r = 0; r < b.n_store; r++) __stcg(b.peer[r] + i, v);
+        }
+    }
+}
+
 // Counter-based draw for the device walk sampler (host mirror: oracle f2vo_counter_rand).
 __host__ __device__ __forceinline__ uint32_t counter_rand(uint64_t seed, uint64_t epoch, uint64_t vertex, uint32_t step) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (vertex * 8u + step + 1u) + 0xD1B54A32D192ED03ULL * (epoch + 1u);

@@ -117,7 +117,11 @@ int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_m
 
 /* Host-buffer epoch (the end-to-end call): upload X_in (nullable = keep resident),
  * the epoch's negatives and walks (nullable), run the epoch, download into X_out
- * (nullable).  Synchronous.                                                           */
+ * (nullable).  Synchronous.  Single GPU: finished rows are copied back while later
+ * minibatches still compute.  Multi-GPU engine with the peer exchange: every rank passes
+ * the same full-size buffers but moves only rows [rank*ceil(n/world), ...) -- its share
+ * -- over its PCIe link (the other replicas receive them over NVLink), and only that
+ * row range of X_out is written on this rank.                                          */
 int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode,
                        float lr, uint32_t chunk, const float* X_in,
                        const uint32_t* neg_idx_host, uint64_t neg_count,

@@ -59,6 +59,20 @@ def main():
                 dist.all_gather_object(blobs, multi.comm_peer_export())
                 multi.comm_peer_init(blobs, rank, world)
             a = run(multi)
+            if comm in ("peer", "peer_unicast"):
+                # host-buffer epochs: every rank moves only its 1/world share of the table over PCIe
+                # (the rest travels over NVLink) and gets its share of the result back
+                per = -(-n // world)
+                lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+                Xin, Xout = X0.copy(), np.zeros_like(X0)
+                for w, neg in streams:
+                    multi.run_epoch_host(model, batch, 5, bs, 0.02, X_in=Xin, neg=neg, walks=w, X_out=Xout, chunk=64)
+                    parts = [None] * world
+                    dist.all_gather_object(parts, Xout[lo:hi].copy())
+                    Xin = np.concatenate(parts)              # the job's result = the ranks' shares
+                if not np.array_equal(Xin, b):
+                    print("rank", rank, comm, "host-buffer epochs differ, model", model, bs, flush=True)
+                    ok = False
             dist.barrier()           # nobody unmaps a table a peer may still be storing into
             multi.close()
             same = np.array_equal(a, b)
