@@ -440,3 +440,32 @@ def test_persistent_epoch_equals_launch_per_minibatch(model, bs, dim, batch, sca
         if mode == 1:
             assert launches == 3                 # one launch per epoch
     assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("model,bs,dim,batch", [(6, 0, 32, 37), (5, 1, 128, 64), (7, 0, 64, 256), (6, 1, 128, 1000)])
+def test_dependent_launch_chaining_is_exact(model, bs, dim, batch):
+    """Programmatic dependent launch lets minibatch b+1 start while b drains; whatever it reads
+    before its dependency wait must be data b cannot have written.  Three epochs with the chaining
+    off (pdl 0), on (pdl 1: wait before the own row) and on with the early own-row read (pdl 2),
+    several times each: all bit-identical."""
+    rp, ci = host.rmat_csr(10, 16, 2)
+    n = len(rp) - 1
+    g = host.RandStream(1)
+    X0 = g.init_embeddings(model, n, dim)
+    streams = []
+    for it in range(3):
+        w = g.walks(rp, ci).copy() if model == 7 else None
+        streams.append((w, g.epoch_negatives(model, n, batch, 5, bs).copy()))
+    ref = None
+    for pdl in (0, 2, 2, 2, 1, 1, 2, 2):
+        with _engine(rp, ci, dim, X0, model) as e:
+            e.set_option("pdl", pdl)
+            for w, neg in streams:
+                if w is not None:
+                    e.set_walks(w)
+                e.set_negatives(neg)
+                e.run_epoch(model, batch, 5, bs, LR)
+            X = e.get_embeddings()
+        if ref is None:
+            ref = X
+        assert np.array_equal(ref, X), pdl
