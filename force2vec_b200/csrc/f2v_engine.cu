@@ -415,8 +415,9 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
     case 128:
         // auto (-1): 4 CTAs/SM at 64 registers; launches with many items run 5 CTAs/SM at 48 registers
         // (a few spilled values, 25 % more gathered rows in flight: measured 5-9 % faster from ~64 K items,
-        // slower below)
-        switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u ? 8 : 3)) {
+        // slower below); small launches are latency-bound, not occupancy-bound, and run 8 rows in
+        // flight per group at 128 registers (5-11 % faster below ~12 K items)
+        switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u ? 8 : (p.n_items < 12000u ? 11 : 3))) {
         case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st, sm_count, persist);
         case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st, sm_count, persist);
         case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count, persist);
@@ -427,6 +428,8 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         case 8: return launch_batch_m<VecL<128, 16, 2, 5>>(model, p, st, sm_count, persist);
         case 9: return launch_batch_m<VecL<128, 16, 2, 6>>(model, p, st, sm_count, persist);
         case 10: return launch_batch_m<VecL<128, 16, 2, 7>>(model, p, st, sm_count, persist);
+        case 11: return launch_batch_m<VecL<128, 16, 8, 2>>(model, p, st, sm_count, persist);
+        case 12: return launch_batch_m<VecL<128, 8, 8, 2>>(model, p, st, sm_count, persist);
         default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st, sm_count, persist);   // 3
         }
     case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st, sm_count, persist);
@@ -441,6 +444,7 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
 }
 
 // ---- persistent epoch kernel (epoch mode 1): cooperative launch, grid = SMs x resident CTAs
+static int g_epoch_ctas_per_sm = 0;     // 0 = as many as fit (tuning knob "epoch_ctas")
 template <class L, int MODEL>
 static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid_out, bool query) {
     auto kern = force_epoch_kernel<L, MODEL>;
@@ -457,6 +461,7 @@ static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (g_epoch_ctas_per_sm > 0) per_sm = std::min(per_sm, g_epoch_ctas_per_sm);
     const unsigned grid = (unsigned)(sm_count * per_sm);
     *grid_out = grid;
     if (query) return cudaSuccess;
@@ -1024,6 +1029,8 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "order")) e->order = (int)value;
     else if (!strcmp(name, "multicast")) e->want_mc = value != 0;
     else if (!strcmp(name, "trace")) e->trace = (int)value;
+    else if (!strcmp(name, "epoch_ctas")) g_epoch_ctas_per_sm = (int)value;
+    else if (!strcmp(name, "min_chunk")) { min_chunk_override() = (uint32_t)std::max<int64_t>(0, value); e->epoch_plan.batch = 0; e->step_plan.batch = 0; }
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }

@@ -22,6 +22,12 @@ struct alignas(16) HubInfo {
 };
 
 constexpr uint32_t kMinChunk = 8;
+// Lower bound of the adaptive chunk length: 16 for minibatches of up to 8192 rows (their launches
+// run the 8-rows-in-flight layout, for which a 16-edge item is two gather iterations), else 8.
+// A function of the batch size only, so every world size / epoch mode cuts hub rows identically.
+inline uint32_t default_min_chunk(uint32_t batch) { return batch <= 8192 ? 16u : kMinChunk; }
+// tuning override ("min_chunk" option; 0 = default_min_chunk)
+inline uint32_t& min_chunk_override() { static uint32_t v = 0; return v; }
 
 // Partial sums of a split row are folded in two levels: blocks of kFoldBlock consecutive chunks,
 // then the block sums.
@@ -115,7 +121,7 @@ inline void owned_rows(const uint64_t* rp, uint64_t first_row, uint64_t nrows, u
 // remaining rows by descending degree class, so the heaviest items are scheduled first.
 // On a multi-GPU engine only the rows of every minibatch that `rank` owns are planned.
 // `par` > 0 makes the chunk length adaptive per minibatch: chunk_b = clamp(edges_b / par,
-// kMinChunk, chunk) with edges_b the edges of the whole minibatch (all ranks), so that a
+// min_chunk, chunk) with edges_b the edges of the whole minibatch (all ranks), so that a
 // minibatch with little work is still cut into enough items to occupy `par` lane groups in one
 // wave and its critical path (the longest item) stays short.
 inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nrows, uint32_t batch,
@@ -140,7 +146,7 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
         uint64_t ch = chunk;
         if (par != 0 && bhi > blo) {
             const uint64_t c = (edges + par - 1) / par;
-            ch = std::min<uint64_t>(chunk, std::max<uint64_t>(std::min<uint64_t>(kMinChunk, chunk), c));
+            ch = std::min<uint64_t>(chunk, std::max<uint64_t>(std::min<uint64_t>(min_chunk_override() ? min_chunk_override() : default_min_chunk(batch), chunk), c));
         }
         chunk_len[b] = ch;
         uint64_t cnt = 0, hubs = 0, slots = 0;

@@ -59,7 +59,7 @@ int  f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t* n, uint64
 /* ---- work plan (exposed for tests of the host-side scheduling / multi-GPU slicing) ----
  * The plan the engine builds for rows [first_row, first_row+nrows) in minibatches of
  * `batch`: per minibatch, hub rows (degree > chunk; with par > 0 the chunk of a minibatch is
- * clamp(edges/par, 8, chunk)) cut into chunks, then the other rows by
+ * clamp(edges/par, batch <= 8192 ? 16 : 8, chunk)) cut into chunks, then the other rows by
  * descending degree class; with world > 1 only the rows of each minibatch that `rank` owns:
  * assign 0 = its contiguous slice of batch/world rows (NCCL all-gather exchange), assign 1 =
  * degree-balanced greedy partition (peer-store exchange); assign | 2 = the lightest rows

@@ -232,7 +232,7 @@ def test_plan_adaptive_chunk():
         lo, hi = int(pl["item_ptr"][b]), int(pl["item_ptr"][b + 1])
         ln = (pl["items"]["len"][lo:hi] & 0x7fffffff).astype(np.int64)
         edges = int(rp[min(len(rp) - 1, (b + 1) * 512)] - rp[b * 512])
-        want = min(64, max(8, -(-edges // 256)))
+        want = min(64, max(16, -(-edges // 256)))      # batch 512 <= 8192: lower bound 16
         assert ln.max() <= want
 
 
