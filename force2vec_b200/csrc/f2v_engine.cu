@@ -411,7 +411,21 @@ static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t 
 static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
     switch (p.dim) {
     case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st, sm_count, persist);
-    case 64: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count, persist);
+    case 64:
+        // auto (-1): small launches run 4 rows in flight per 8-lane group (104 registers: latency-bound);
+        // large ones 2 rows in flight at 64 registers / 4 CTAs per SM, the walk model (every item has
+        // 5 + s pairs: occupancy-bound) at 48 registers / 5 CTAs per SM -- measured on R-MAT 20/22:
+        // option 7 2.42 -> 1.46 ms, option 6 1.41 -> 1.22 ms per epoch at batch 65536
+        // (batch 16384, option 7: 2.82 / 1.90 / 2.09 ms for the three layouts; batch 4096: 5.76 / 6.72 / 7.03)
+        switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u && model == kWalk ? 4 : (p.n_items >= 8000u ? 1 : 0))) {
+        case 1: return launch_batch_m<VecL<64, 8, 2, 4>>(model, p, st, sm_count, persist);
+        case 2: return launch_batch_m<VecL<64, 16, 4, 4>>(model, p, st, sm_count, persist);
+        case 3: return launch_batch_m<VecL<64, 16, 2, 5>>(model, p, st, sm_count, persist);
+        case 4: return launch_batch_m<VecL<64, 8, 2, 5>>(model, p, st, sm_count, persist);
+        case 5: return launch_batch_m<VecL<64, 16, 4, 5>>(model, p, st, sm_count, persist);
+        case 6: return launch_batch_m<VecL<64, 8, 4, 3>>(model, p, st, sm_count, persist);
+        default: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count, persist);
+        }
     case 128:
         // auto (-1): 4 CTAs/SM at 64 registers; launches with many items run 5 CTAs/SM at 48 registers
         // (a few spilled values, 25 % more gathered rows in flight: measured 5-9 % faster from ~64 K items,
