@@ -1041,7 +1041,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;
     else if (!strcmp(name, "pdl")) e->pdl = (int)value;
     else if (!strcmp(name, "order")) e->order = (int)value;
-    else if (!strcmp(name, "multicast")) e->want_mc = value != 0;
+    else if (!strcmp(name, "multicast")) e->want_mc = (int)value;
     else if (!strcmp(name, "trace")) e->trace = (int)value;
     else if (!strcmp(name, "epoch_ctas")) g_epoch_ctas_per_sm = (int)value;
     else if (!strcmp(name, "min_chunk")) { min_chunk_override() = (uint32_t)std::max<int64_t>(0, value); e->epoch_plan.batch = 0; e->step_plan.batch = 0; }
@@ -1182,9 +1182,15 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
     auto close_all = [&]() { for (int k = 0; k < kMaxWorld; k++) if (conns[k] >= 0) { close(conns[k]); conns[k] = -1; } };
     CUmemGenericAllocationHandle mc = 0;
     if (rank == 0) {
-        DRV(g_drv.MulticastCreate(&mc, &mp));
+        // if the object cannot be created here (e.g. the fabric does not offer multicast to this
+        // set of devices) every rank is told so and the caller falls back to unicast peer stores
         int fd = -1;
-        DRV(g_drv.MemExportToShareableHandle(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+        bool have = e->want_mc != 2 &&            // option multicast = 2: exercise the fall-back (tests)
+                    g_drv.MulticastCreate(&mc, &mp) == CUDA_SUCCESS;
+        if (have && g_drv.MemExportToShareableHandle(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) {
+            g_drv.MemRelease(mc);
+            have = false;
+        }
         for (int k = 1; k < world; k++) {
             int c = accept(e->listen_sock, nullptr, nullptr);
             char who = 0;
@@ -1195,6 +1201,9 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
             }
             conns[(int)who] = c;
         }
+        for (int k = 1; k < world; k++)
+            if (sock_byte(conns[k], true, have ? 'Y' : 'N')) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: send failed"); }
+        if (!have) { close_all(); return F2V_OK; }      // e->mc_mode stays false
         for (int k = 1; k < world; k++)
             if (sock_send_fd(conns[k], fd) != 0) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: cannot send the handle"); }
         close(fd);
@@ -1213,6 +1222,9 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
         conns[0] = c;
         char who = (char)rank;
         if (send(c, &who, 1, 0) != 1) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: send failed"); }
+        char have = 0;
+        if (recv(c, &have, 1, MSG_WAITALL) != 1) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: no answer from rank 0"); }
+        if (have != 'Y') { close_all(); return F2V_OK; }  // rank 0 could not create the object: unicast
         int fd = sock_recv_fd(c);
         if (fd < 0) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: no handle received"); }
         CUresult ir = g_drv.MemImportFromShareableHandle(&mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
@@ -1286,6 +1298,8 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
         if (mc) {
             int rr = mc_setup(e, all, rank, world);
             if (rr) return rr;
+        }
+        if (mc && e->mc_mode) {
             e->rank = rank;
             e->world = world;
             e->peer_mode = true;

@@ -44,12 +44,15 @@ def main():
         b = run(single)
         single.close()
         # peer: NVLink multicast stores where the box supports them; peer_unicast: one store per peer
-        for comm in ("peer", "peer_unicast", "peer_persistent", "nccl"):
+        # peer_fallback: rank 0 reports that the multicast object cannot be created -> all ranks go unicast
+        for comm in ("peer", "peer_unicast", "peer_fallback", "peer_persistent", "nccl"):
             multi = F.Engine(rp, ci, dim, device=local)
             if comm == "peer_persistent":
                 multi.set_epoch_mode(1)          # one cooperative launch per epoch, exchange barrier inside
             if comm == "peer_unicast":
                 multi.set_option("multicast", 0)
+            if comm == "peer_fallback":
+                multi.set_option("multicast", 2)
             if comm == "nccl":
                 ids = [F.Engine.comm_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(ids, src=0)
