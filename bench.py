@@ -51,6 +51,7 @@ def parse():
                     help="N>1 exchange: peer = stores into the peers' replicas fused into the force kernel; "
                          "nccl = all-gather per minibatch (baseline)")
     ap.add_argument("--multicast", type=int, default=1, help="peer exchange through NVLink multicast (NVLS) stores")
+    ap.add_argument("--sharded", type=int, default=0, help="N>1: row-sharded tables instead of replicas (capacity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra-batches", default="256,4096,16384", help="comma list of additional batch sizes to report")
@@ -281,6 +282,7 @@ def run_ours(a):
         eng.comm_init(ids[0], rank, world)
     elif world > 1:
         eng.set_option("multicast", a.multicast)
+        eng.set_option("sharded", a.sharded)
         blobs = [None] * world
         dist.all_gather_object(blobs, eng.comm_peer_export())
         eng.comm_peer_init(blobs, rank, world)
@@ -341,7 +343,7 @@ def run_ours(a):
         # bytes over PCIe per step, whole job: with the peer exchange every rank moves 1/world of the
         # table each way (NCCL mode: every rank moves the whole table)
         tbl = n * a.dim * 4
-        copies = 1 if (world == 1 or a.comm == "peer") else world
+        copies = 1 if (world == 1 or (a.comm == "peer" and not a.sharded)) else world
         e2e = {"value": pairs / (e2e_sec / K), "unit": "pairs/s",
                "h2d_bytes_per_step": int(tbl * copies + stride * 4 * world), "d2h_bytes_per_step": int(tbl * copies),
                "ms_per_step": e2e_sec / K * 1e3,
@@ -383,8 +385,10 @@ def run_ours(a):
                            "init": "glibc-compatible srand(1) stream (reference order)",
                            "parallelism": "replicated table, minibatch split over %d rank(s)%s" %
                                           (world, "" if world == 1 else (", NCCL all-gather per minibatch" if a.comm == "nccl" else
+                                                      (", row-sharded tables (1/%d of the rows per GPU, remote gathers over NVLink"
+                                                       " + flag barrier per minibatch)" % world) if a.sharded else
                                                       ", rows stored into the peers' replicas from the force kernel "
-                                                      "(NVLink peer stores + flag barrier per minibatch)"))},
+                                                      "(NVLink multicast / peer stores + flag barrier per minibatch)"))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "epoch_s": epoch_s, "extra": extra}
         print(json.dumps(line), flush=True)

@@ -249,6 +249,15 @@ struct f2v_engine {
     size_t vmm_size = 0;
     int listen_sock = -1;
     char sock_name[48] = "";
+    // row-sharded tables: one flat virtual range, shard s = physical memory of rank s (VMM), mapped
+    // on every rank; see shard_row() in f2v_kernels.cuh
+    int want_shard = 0;                      // option "sharded"
+    bool shard_mode = false;
+    uint32_t shard_lg = 0, shard_rows = 0;
+    CUmemGenericAllocationHandle shard_handles[2][kMaxWorld] = {};   // [table][rank]
+    CUdeviceptr shard_va = 0;
+    size_t shard_bytes = 0;                  // bytes of one shard of one table
+    float* d_shard_stage = nullptr;          // staging chunk for host <-> sharded table copies
     int trace = 0;                           // option "trace": one CUDA event per minibatch of the last epoch
     std::vector<cudaEvent_t> trace_ev;
     uint64_t trace_n = 0;
@@ -269,8 +278,9 @@ struct PeerBlob {
     uint64_t rows_alloc;
     uint64_t ptr[2];                         // tables (X[0] then X[1]), flags (valid inside process `pid`)
     cudaIpcMemHandle_t h[2];
+    uint32_t shard;                          // this rank wants row-sharded tables (option "sharded")
     uint32_t mc_ok;                          // this rank can and wants to use NVLink multicast
-    char sock_name[44];                      // abstract unix socket this rank listens on (fd hand-off)
+    char sock_name[40];                      // abstract unix socket this rank listens on (fd hand-off)
 };
 static_assert(sizeof(PeerBlob) <= F2V_PEER_BLOB, "PeerBlob must fit the ABI's blob size");
 constexpr uint32_t kPeerMagic = 0x46325650u;
@@ -302,6 +312,11 @@ static int alloc_tables(f2v_engine* e, uint64_t rows) {
     e->d_X[1] = all + rows * e->dim;
     e->rows_alloc = rows;
     return F2V_OK;
+}
+
+static int ensure_tables(f2v_engine* e) {
+    if (e->d_Xall) return F2V_OK;
+    return alloc_tables(e, e->rows_alloc ? e->rows_alloc : e->n);
 }
 
 // Upload the host plan (f2v_plan.hpp) for rows [first_row, first_row+nrows) and size the
@@ -530,6 +545,64 @@ static uint64_t neg_stride(int model, uint32_t batch, uint32_t s, int bs_mode) {
     return (bs_mode && model != F2V_WALK) ? (uint64_t)batch + s - 1 : (uint64_t)s;
 }
 
+// Row-sharded engine: rows [first, first+count) of the live table <-> a host buffer in identity
+// layout, through a device staging chunk (the flat table is a permutation spread over all GPUs).
+static int shard_copy(f2v_engine* e, bool to_table, uint64_t first, uint64_t count, float* host) {
+    if (!to_table && e->step_id) {
+        // reading other ranks' shards: wait until every rank has published the current exchange step
+        BatchParams p{};
+        p.n_peers = (uint32_t)(e->world - 1);
+        p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
+        p.flags = e->d_flags; p.done = e->d_done;
+        p.wait_step = e->step_id;
+        peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * e->dim));
+    if (!e->d_shard_stage) CU(cudaMalloc((void**)&e->d_shard_stage, sizeof(float) * chunk_rows * e->dim));
+    float* table = e->d_X[e->cur];
+    for (uint64_t a = 0; a < count; a += chunk_rows) {
+        const uint64_t c = std::min(chunk_rows, count - a);
+        const size_t bytes = sizeof(float) * c * e->dim;
+        const unsigned grid = (unsigned)std::min<uint64_t>((c * e->dim + 255) / 256, (uint64_t)e->sm_count * 16);
+        if (to_table) {
+            CU(cudaMemcpyAsync(e->d_shard_stage, host + a * e->dim, bytes, cudaMemcpyHostToDevice, e->stream));
+            shard_copy_kernel<true><<<grid, 256, 0, e->stream>>>(table, e->d_shard_stage, first + a, c, e->dim, e->shard_lg,
+                                                                  e->shard_rows, (uint32_t)e->rank);
+        } else {
+            shard_copy_kernel<false><<<grid, 256, 0, e->stream>>>(table, e->d_shard_stage, first + a, c, e->dim, e->shard_lg,
+                                                                   e->shard_rows, (uint32_t)e->rank);
+            CU(cudaMemcpyAsync(host + a * e->dim, e->d_shard_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));        // one staging chunk: finish before it is reused
+    }
+    return F2V_OK;
+}
+
+// Publish one exchange step outside an epoch (after a sharded upload / a broadcast of uploaded
+// rows): every rank must do it the same number of times.
+static int publish_exchange_step(f2v_engine* e) {
+    BatchParams p{};
+    p.n_peers = (uint32_t)(e->world - 1);
+    p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
+    p.flags = e->d_flags; p.done = e->d_done;
+    if (e->mc_mode) {
+        p.mc_flag = (uint64_t*)((char*)e->vmm_mc + ((char*)e->d_flags - (char*)e->d_Xall)) + (size_t)e->rank * kFlagStride;
+    } else {
+        for (int q = 0, k = 0; q < e->world; q++) {
+            if (q == e->rank) continue;
+            p.peer_flag[k++] = e->peer_flags[q] + (size_t)e->rank * kFlagStride;
+        }
+    }
+    p.wait_step = 0;
+    p.signal_step = ++e->step_id;
+    peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
+    CU(cudaGetLastError());
+    e->launches++;
+    return F2V_OK;
+}
+
 // ------------------------------------------------------------------ C ABI --------------
 extern "C" {
 
@@ -577,7 +650,8 @@ int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz, const 
     CU(cudaMalloc((void**)&e->d_colids, sizeof(uint32_t) * (nnz ? nnz : 1)));
     CU(cudaMemcpy(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice));
     if (nnz) CU(cudaMemcpy(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
-    { int r = alloc_tables(e, n); if (r) { f2v_destroy(e); return r; } }
+    e->rows_alloc = n;                       // tables are allocated on first use (ensure_tables): a row-sharded
+                                             // engine never holds a full-size table
     CU(cudaMalloc((void**)&e->d_lut, sizeof(float) * kLutAlloc));
     *out = e;
     return F2V_OK;
@@ -590,7 +664,7 @@ int f2v_destroy(f2v_engine* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (int r = 0; r < kMaxWorld; r++) {
         if (!e->peer_ipc[r]) continue;
-        cudaIpcCloseMemHandle(e->peerX[r][0]);
+        if (e->peerX[r][0]) cudaIpcCloseMemHandle(e->peerX[r][0]);
         cudaIpcCloseMemHandle(e->peer_flags[r]);
     }
     if (e->listen_sock >= 0) close(e->listen_sock);
@@ -607,6 +681,14 @@ int f2v_destroy(f2v_engine* e) {
         g_drv.MemRelease(e->mc_handle);
         e->d_Xall = nullptr; e->d_flags = nullptr;
     }
+    if (e->shard_mode) {
+        const size_t total = 2 * (size_t)e->world * e->shard_bytes;
+        g_drv.MemUnmap(e->shard_va, total);
+        g_drv.MemAddressFree(e->shard_va, total);
+        for (int s = 0; s < e->world; s++) { g_drv.MemRelease(e->shard_handles[0][s]); g_drv.MemRelease(e->shard_handles[1][s]); }
+        e->d_Xall = nullptr;
+    }
+    cudaFree(e->d_shard_stage);
     cudaFree(e->d_flags); cudaFree(e->d_done);
     cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_Xall);
     cudaFree(e->d_lut); cudaFree(e->d_neg); cudaFree(e->d_walks); cudaFree(e->d_stage);
@@ -654,6 +736,14 @@ int f2v_sync(f2v_engine* e) {
 int f2v_set_embeddings(f2v_engine* e, const float* X) {
     if (!e || !X) return fail(F2V_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
+    if (e->shard_mode) {
+        // this rank fills its own shard; the other shards are filled by their ranks, so the upload
+        // ends with one exchange step: the next epoch's first launch waits for every rank's step
+        int r = shard_copy(e, true, 0, e->n, const_cast<float*>(X));
+        if (r) return r;
+        return publish_exchange_step(e);
+    }
+    { int r = ensure_tables(e); if (r) return r; }
     CU(cudaMemcpyAsync(e->d_X[e->cur], X, sizeof(float) * e->n * e->dim, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return F2V_OK;
@@ -662,6 +752,8 @@ int f2v_set_embeddings(f2v_engine* e, const float* X) {
 int f2v_get_embeddings(f2v_engine* e, float* X) {
     if (!e || !X) return fail(F2V_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
+    if (e->shard_mode) return shard_copy(e, false, 0, e->n, X);     // remote shards are read over NVLink
+    { int r = ensure_tables(e); if (r) return r; }
     CU(cudaMemcpyAsync(X, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return F2V_OK;
@@ -671,6 +763,8 @@ int f2v_get_rows(f2v_engine* e, uint64_t first_row, uint64_t nrows, float* rows)
     if (!e || !rows) return fail(F2V_ERR_ARG, "null argument");
     if (first_row + nrows > e->n) return fail(F2V_ERR_ARG, "row range out of bounds");
     CU(cudaSetDevice(e->device));
+    if (e->shard_mode) return shard_copy(e, false, first_row, nrows, rows);
+    { int r = ensure_tables(e); if (r) return r; }
     CU(cudaMemcpyAsync(rows, e->d_X[e->cur] + first_row * e->dim, sizeof(float) * nrows * e->dim,
                        cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -755,7 +849,9 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
              uint32_t s, int bs_mode, float lr, const uint32_t* walks) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
     if (model == F2V_WALK) bs_mode = 0;     // -bs is ignored by option 7 (Test/Force2Vec.cpp:148-150)
+    if (e->shard_mode) return fail(F2V_ERR_STATE, "f2v_step is a single-engine test entry point; not available on a row-sharded engine");
     CU(cudaSetDevice(e->device));
+    { int r0 = ensure_tables(e); if (r0) return r0; }
     if (model == F2V_WALK && walks) { int r = f2v_set_walks(e, walks); if (r) return r; }
     int r = check_model(e, model, s, bs_mode);
     if (r) return r;
@@ -811,11 +907,14 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
                     (unsigned long long)e->neg_count, (unsigned long long)e->neg_off, (unsigned long long)(nb * W));
     // tables: the all-gather works on whole minibatches, so pad the row count to nb*batch
     const uint64_t rows_needed = (e->world > 1 && !e->peer_mode) ? nb * batch : e->n;
-    if (e->rows_alloc < rows_needed) {
+    if (!e->shard_mode && e->rows_alloc < rows_needed) {
         CU(cudaStreamSynchronize(e->stream));
         r = alloc_tables(e, rows_needed);
         if (r) return r;
     }
+    r = ensure_tables(e);
+    if (r) return r;
+    if (e->shard_mode && e->epoch_mode != 0) return fail(F2V_ERR_STATE, "row-sharded engines run epoch mode 0");
     const int order = e->order >= 0 ? e->order : (e->peer_mode ? 1 : 0);
     r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world,
                    (e->peer_mode ? kAssignBalanced : kAssignSlices) | (order == 1 ? kOrderLightFirst : 0) | (order == 2 ? kOrderInterleave : 0));
@@ -836,7 +935,8 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     const uint64_t slice = batch / (uint64_t)e->world;
     if (e->peer_mode) {
         p.n_peers = (e->peer_debug & 2) ? 0u : (uint32_t)(e->world - 1);
-        p.n_store = ((e->peer_debug & 1) || e->mc_mode) ? 0u : (uint32_t)(e->world - 1);
+        p.n_store = ((e->peer_debug & 1) || e->mc_mode || e->shard_mode) ? 0u : (uint32_t)(e->world - 1);
+        if (e->shard_mode) { p.shard_lg = e->shard_lg; p.shard_rows = e->shard_rows; }
         if (e->mc_mode) {
             // the same offsets inside the multicast mapping: one store reaches every replica
             p.mc_out = (float*)((char*)e->vmm_mc + ((char*)Xnew - (char*)e->d_Xall));
@@ -846,7 +946,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         p.flags = e->d_flags; p.done = e->d_done;
         for (int r = 0, k = 0; r < e->world && !e->mc_mode; r++) {
             if (r == e->rank) continue;
-            p.peer_out[k] = e->peerX[r][1 - e->cur];
+            p.peer_out[k] = e->shard_mode ? nullptr : e->peerX[r][1 - e->cur];
             p.peer_flag[k] = e->peer_flags[r] + (size_t)e->rank * kFlagStride;
             k++;
         }
@@ -957,6 +1057,17 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
     if (!e) return fail(F2V_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     int r;
+    if (e->shard_mode) {
+        if (X_in) { r = f2v_set_embeddings(e, X_in); if (r) return r; }
+        if (neg) { r = f2v_set_negatives(e, neg, neg_count); if (r) return r; }
+        if (walks) { r = f2v_set_walks(e, walks); if (r) return r; }
+        r = run_epoch_impl(e, model, batch, s, bs_mode, lr, chunk, nullptr);
+        if (r) return r;
+        CU(cudaStreamSynchronize(e->stream));
+        if (X_out) { r = f2v_get_embeddings(e, X_out); if (r) return r; }
+        return F2V_OK;
+    }
+    { r = ensure_tables(e); if (r) return r; }
     // multi-GPU with the peer exchange: rank r moves only rows [lo, hi) = its 1/world share of the
     // table over PCIe, in both directions; the other replicas get them over NVLink
     const bool sharded = e->peer_mode && e->world > 1;
@@ -990,23 +1101,8 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
             e->launches++;
         }
         // publish: one exchange step; the epoch's first minibatch waits for every rank's rows
-        BatchParams p{};
-        p.n_peers = (uint32_t)(e->world - 1);
-        p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
-        p.flags = e->d_flags; p.done = e->d_done;
-        if (e->mc_mode) {
-            p.mc_flag = (uint64_t*)((char*)e->vmm_mc + ((char*)e->d_flags - (char*)e->d_Xall)) + (size_t)e->rank * kFlagStride;
-        } else {
-            for (int q = 0, k = 0; q < e->world; q++) {
-                if (q == e->rank) continue;
-                p.peer_flag[k++] = e->peer_flags[q] + (size_t)e->rank * kFlagStride;
-            }
-        }
-        p.wait_step = 0;
-        p.signal_step = ++e->step_id;
-        peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
-        CU(cudaGetLastError());
-        e->launches++;
+        r = publish_exchange_step(e);
+        if (r) return r;
     }
     if (neg) { r = f2v_set_negatives(e, neg, neg_count); if (r) return r; }
     if (walks) { r = f2v_set_walks(e, walks); if (r) return r; }
@@ -1043,6 +1139,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "order")) e->order = (int)value;
     else if (!strcmp(name, "multicast")) e->want_mc = (int)value;
     else if (!strcmp(name, "trace")) e->trace = (int)value;
+    else if (!strcmp(name, "sharded")) e->want_shard = value != 0;
     else if (!strcmp(name, "epoch_ctas")) g_epoch_ctas_per_sm = (int)value;
     else if (!strcmp(name, "min_chunk")) { min_chunk_override() = (uint32_t)std::max<int64_t>(0, value); e->epoch_plan.batch = 0; e->step_plan.batch = 0; }
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
@@ -1112,14 +1209,16 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
     b.magic = kPeerMagic; b.device = e->device; b.pid = (uint64_t)getpid();
     b.n = e->n; b.dim = e->dim; b.cur = (uint64_t)e->cur;
     b.rows_alloc = e->rows_alloc;
+    b.shard = e->want_shard ? 1u : 0u;
+    if (!e->want_shard) { int r = ensure_tables(e); if (r) return r; }
     void* ptrs[2] = {e->d_Xall, e->d_flags};
-    for (int k = 0; k < 2; k++) {
+    for (int k = e->want_shard ? 1 : 0; k < 2; k++) {      // a sharded engine exports its flag page only
         b.ptr[k] = (uint64_t)(uintptr_t)ptrs[k];
         CU(cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
     }
     // NVLink multicast: can this device do it, and is a hand-off socket up?
     b.mc_ok = 0;
-    if (e->want_mc && drv_load() == F2V_OK) {
+    if ((e->want_mc || e->want_shard) && drv_load() == F2V_OK) {
         CUdevice dev;
         int mc = 0, posix = 0;
         if (g_drv.DeviceGet(&dev, e->device) == CUDA_SUCCESS &&
@@ -1273,6 +1372,150 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
     return F2V_OK;
 }
 
+// Row-sharded tables.  Every rank creates the physical memory of its shard (both tables) with the
+// VMM API, the file descriptors are collected by rank 0 and handed to everybody over the unix
+// socket, and every rank maps all shards into one flat virtual range: table t, shard s at
+// ((t * world + s) * shard_bytes).  A gather of a remote shard's row is then an ordinary load that
+// travels over NVLink; the kernels only permute the row index (shard_row()).
+static int shard_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
+    int r = drv_load();
+    if (r) return r;
+    uint32_t lg = 0;
+    while ((1 << lg) < world) lg++;
+    if ((1 << lg) != world) return fail(F2V_ERR_ARG, "row-sharded tables need a power-of-two world size (got %d)", world);
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = e->device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    DRV(g_drv.MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    const size_t row_bytes = sizeof(float) * e->dim;
+    // rows per shard: ceil(n / world) rounded up until the shard is a whole number of granules
+    uint64_t rows = (e->n + (uint64_t)world - 1) / (uint64_t)world;
+    size_t g = gran, rb = row_bytes;
+    while (rb) { size_t t = g % rb; g = rb; rb = t; }            // g = gcd(gran, row_bytes)
+    const uint64_t step = gran / g;                              // rows per smallest granule-aligned block
+    rows = (rows + step - 1) / step * step;
+    if (2ull * rows * world > 0xffffffffull) return fail(F2V_ERR_ARG, "sharded table too large for 32-bit row ids");
+    const size_t shard_bytes = rows * row_bytes;
+
+    // one physical allocation per table (cuMemMap maps whole allocations only)
+    CUmemGenericAllocationHandle mine[2] = {0, 0};
+    int fds[2][kMaxWorld];
+    for (int t = 0; t < 2; t++)
+        for (int k = 0; k < kMaxWorld; k++) fds[t][k] = -1;
+    for (int t = 0; t < 2; t++) {
+        DRV(g_drv.MemCreate(&mine[t], shard_bytes, &ap, 0));
+        DRV(g_drv.MemExportToShareableHandle(&fds[t][rank], mine[t], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    }
+    int conns[kMaxWorld];
+    for (int k = 0; k < kMaxWorld; k++) conns[k] = -1;
+    auto close_all = [&]() {
+        for (int k = 0; k < kMaxWorld; k++) {
+            if (conns[k] >= 0) close(conns[k]);
+            conns[k] = -1;
+            for (int t = 0; t < 2; t++) { if (fds[t][k] >= 0) close(fds[t][k]); fds[t][k] = -1; }
+        }
+    };
+    if (rank == 0) {
+        for (int k = 1; k < world; k++) {
+            int c = accept(e->listen_sock, nullptr, nullptr);
+            char who = 0;
+            if (c < 0 || recv(c, &who, 1, MSG_WAITALL) != 1 || who < 1 || who >= world || conns[(int)who] >= 0) {
+                if (c >= 0) close(c);
+                close_all();
+                return fail(F2V_ERR_STATE, "shard hand-off: bad connection");
+            }
+            conns[(int)who] = c;
+            for (int t = 0; t < 2; t++) {
+                fds[t][(int)who] = sock_recv_fd(c);
+                if (fds[t][(int)who] < 0) { close_all(); return fail(F2V_ERR_STATE, "shard hand-off: no handle from rank %d", (int)who); }
+            }
+        }
+        for (int k = 1; k < world; k++)
+            for (int q = 0; q < world; q++)
+                for (int t = 0; t < 2; t++)
+                    if (q != k && sock_send_fd(conns[k], fds[t][q]) != 0) { close_all(); return fail(F2V_ERR_STATE, "shard hand-off: send failed"); }
+    } else {
+        int c = socket(AF_UNIX, SOCK_STREAM, 0);
+        struct sockaddr_un a;
+        socklen_t alen;
+        sock_addr(&a, &alen, blobs[0].sock_name);
+        bool up = false;
+        for (int tries = 0; tries < 600 && c >= 0; tries++) {
+            if (connect(c, (struct sockaddr*)&a, alen) == 0) { up = true; break; }
+            struct timespec ts = {0, 100 * 1000 * 1000};
+            nanosleep(&ts, nullptr);
+        }
+        if (!up) { if (c >= 0) close(c); close_all(); return fail(F2V_ERR_STATE, "shard hand-off: rank 0 is not reachable"); }
+        conns[0] = c;
+        char who = (char)rank;
+        if (send(c, &who, 1, 0) != 1 || sock_send_fd(c, fds[0][rank]) != 0 || sock_send_fd(c, fds[1][rank]) != 0) {
+            close_all();
+            return fail(F2V_ERR_STATE, "shard hand-off: send failed");
+        }
+        for (int q = 0; q < world; q++) {
+            if (q == rank) continue;
+            for (int t = 0; t < 2; t++) {
+                fds[t][q] = sock_recv_fd(c);
+                if (fds[t][q] < 0) { close_all(); return fail(F2V_ERR_STATE, "shard hand-off: handle of rank %d missing", q); }
+            }
+        }
+    }
+    auto handshake = [&](char tag) -> int {
+        if (rank == 0) {
+            for (int k = 1; k < world; k++) if (sock_byte(conns[k], false, tag)) return -1;
+            for (int k = 1; k < world; k++) if (sock_byte(conns[k], true, (char)(tag + 1))) return -1;
+            return 0;
+        }
+        if (sock_byte(conns[0], true, tag)) return -1;
+        return sock_byte(conns[0], false, (char)(tag + 1));
+    };
+    CUdeviceptr va = 0;
+    const size_t total = 2 * (size_t)world * shard_bytes;
+    DRV(g_drv.MemAddressReserve(&va, total, gran, 0, 0));
+    for (int s = 0; s < world; s++) {
+        for (int t = 0; t < 2; t++) {
+            CUmemGenericAllocationHandle h = mine[t];
+            if (s != rank) {
+                CUresult ir = g_drv.MemImportFromShareableHandle(&h, (void*)(uintptr_t)fds[t][s], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+                if (ir != CUDA_SUCCESS) { close_all(); return fail(F2V_ERR_CUDA, "cuMemImportFromShareableHandle (shard %d) failed (%d)", s, (int)ir); }
+            }
+            e->shard_handles[t][s] = h;
+            DRV(g_drv.MemMap(va + ((size_t)t * world + s) * shard_bytes, shard_bytes, 0, h, 0));
+        }
+    }
+    CUmemAccessDesc ad;
+    memset(&ad, 0, sizeof(ad));
+    ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = e->device; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    DRV(g_drv.MemSetAccess(va, total, &ad, 1));
+    // zero this rank's shard, then move any live state over (only the rows this rank stores)
+    for (int t = 0; t < 2; t++) CU(cudaMemset((void*)(va + ((size_t)t * world + rank) * shard_bytes), 0, shard_bytes));
+    float* old_all = e->d_Xall;
+    float* old_live = e->d_Xall ? e->d_X[e->cur] : nullptr;
+    e->shard_va = va; e->shard_bytes = shard_bytes; e->shard_lg = lg; e->shard_rows = (uint32_t)rows;
+    e->d_Xall = (float*)va;
+    e->rows_alloc = rows * (uint64_t)world;
+    e->d_X[0] = e->d_Xall;
+    e->d_X[1] = e->d_Xall + e->rows_alloc * e->dim;
+    e->rank = rank;
+    if (old_live) {
+        const uint64_t cells = e->n * e->dim;
+        const unsigned grid = (unsigned)std::min<uint64_t>((cells + 255) / 256, (uint64_t)e->sm_count * 16);
+        shard_copy_kernel<true><<<grid, 256, 0, e->stream>>>(e->d_X[e->cur], old_live, 0, e->n, e->dim, lg, (uint32_t)rows, (uint32_t)rank);
+        CU(cudaGetLastError());
+    }
+    CU(cudaDeviceSynchronize());
+    if (old_all) CU(cudaFree(old_all));
+    e->shard_mode = true;
+    // nobody reads a shard before its owner has zeroed / filled it
+    if (handshake('S')) { close_all(); return fail(F2V_ERR_STATE, "shard hand-off: final handshake failed"); }
+    close_all();
+    return F2V_OK;
+}
+
 int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
     if (!e || !blobs) return fail(F2V_ERR_ARG, "null argument");
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
@@ -1286,6 +1529,7 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
     if (world > 1) {
         PeerBlob all[kMaxWorld];
         bool mc = true;
+        int nshard = 0;
         for (int r = 0; r < world; r++) {
             memcpy(&all[r], (const char*)blobs + (size_t)r * F2V_PEER_BLOB, sizeof(PeerBlob));
             if (all[r].magic != kPeerMagic) return fail(F2V_ERR_ARG, "blob %d is not a peer blob", r);
@@ -1293,7 +1537,16 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
                 return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
             if (all[r].cur != (uint64_t)e->cur) return fail(F2V_ERR_STATE, "rank %d is at a different table parity", r);
             mc = mc && all[r].mc_ok != 0;
+            nshard += all[r].shard != 0;
             for (int q = 0; q < r; q++) mc = mc && all[q].pid != all[r].pid;
+        }
+        if (nshard != 0 && nshard != world) return fail(F2V_ERR_ARG, "the option \"sharded\" must be set on every rank or on none");
+        if (nshard) {
+            // row-sharded tables: needs the VMM hand-off (separate processes, file-descriptor handles)
+            if (!mc) return fail(F2V_ERR_STATE, "row-sharded tables need one process per GPU and VMM file-descriptor handles");
+            int rr = shard_setup(e, all, rank, world);
+            if (rr) return rr;
+            mc = false;                        // rows are stored once, in their shard: nothing to multicast
         }
         if (mc) {
             int rr = mc_setup(e, all, rank, world);
@@ -1312,10 +1565,19 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
         PeerBlob b;
         memcpy(&b, (const char*)blobs + (size_t)r * F2V_PEER_BLOB, sizeof(b));
         if (b.magic != kPeerMagic) return fail(F2V_ERR_ARG, "blob %d is not a peer blob", r);
-        if (b.n != e->n || b.dim != e->dim || b.rows_alloc != e->rows_alloc) return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
+        if (b.n != e->n || b.dim != e->dim || (!e->shard_mode && b.rows_alloc != e->rows_alloc))
+            return fail(F2V_ERR_ARG, "rank %d holds a different table (n or dim)", r);
         if (b.cur != (uint64_t)e->cur) return fail(F2V_ERR_STATE, "rank %d is at a different table parity", r);
         if (r == rank) {
-            if (b.ptr[0] != (uint64_t)(uintptr_t)e->d_Xall) return fail(F2V_ERR_ARG, "blob %d is not this engine's", r);
+            if (!e->shard_mode && b.ptr[0] != (uint64_t)(uintptr_t)e->d_Xall) return fail(F2V_ERR_ARG, "blob %d is not this engine's", r);
+            continue;
+        }
+        if (e->shard_mode) {
+            // only the exchange flags are mapped through IPC; the tables are the flat VMM range
+            void* m = nullptr;
+            CU(cudaIpcOpenMemHandle(&m, b.h[1], cudaIpcMemLazyEnablePeerAccess));
+            e->peer_flags[r] = (uint64_t*)m;
+            e->peer_ipc[r] = true;
             continue;
         }
         if (b.pid == me) {

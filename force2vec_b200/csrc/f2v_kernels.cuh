@@ -56,6 +56,12 @@ struct BatchParams {
     uint32_t split;
     uint32_t off_lo, off_hi;
     const float* Xb;
+    // Row-sharded tables (multi-GPU, tables too large for one GPU): the combined table is ONE flat
+    // virtual range whose shard s (shard_rows rows of each table) is physical memory of GPU s,
+    // mapped on every rank; vertex j lives in shard xorfold(j) & (W-1) at local row j >> shard_lg.
+    // shard_lg = 0: not sharded (row = vertex id).
+    uint32_t shard_lg;
+    uint32_t shard_rows;
     float* out;
     uint64_t out_base;    // out row of vertex v = out + (v - out_base) * dim
     const uint32_t* colids;
@@ -104,6 +110,21 @@ struct BatchVar {
 };
 __device__ __forceinline__ BatchVar batch_var(const BatchParams& p) {
     return BatchVar{p.items, p.hub, p.n_items, p.split, (uint32_t)p.lo, p.neg};
+}
+
+// Vertex id -> row of a table.  Sharded: shard(j) * shard_rows + (j >> lg), where shard(j) is the
+// XOR of all lg-bit digits of j: a bijection between the low digit and the shard for any fixed
+// high part (so (shard, j >> lg) is unique), and unlike j mod W it spreads R-MAT's hubs -- ids with
+// few one-bits, nearly all congruent 0 mod W -- over the GPUs.
+__host__ __device__ __forceinline__ uint32_t shard_row(uint32_t j, uint32_t lg, uint32_t shard_rows) {
+    if (lg == 0) return j;
+    uint32_t f = j;
+    for (uint32_t s = lg; s < 32; s += lg) f ^= j >> s;
+    return (f & ((1u << lg) - 1u)) * shard_rows + (j >> lg);
+}
+// Row of the combined (both tables) range that holds vertex j for a launch with the given split.
+__device__ __forceinline__ uint32_t table_row(const BatchParams& p, uint32_t j, uint32_t split) {
+    return shard_row(j, p.shard_lg, p.shard_rows) + (j < split ? p.off_lo : p.off_hi);
 }
 
 // One persistent launch per epoch (f2v_set_epoch_mode 1): every CTA loops over the minibatches,
@@ -443,13 +464,12 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
     const float* const Xb = p.Xb;
-    const uint32_t off_lo = p.off_lo, off_hi = p.off_hi;
     const uint32_t cnt_max = L::G > 1 ? warp_max(cnt) : cnt;
     for (uint32_t base = 0; base < cnt_max; base += LPR) {
         const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
         const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
         uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldg(idx + base + l) : self);
-        mine += mine < split ? off_lo : off_hi;          // row of the combined table
+        mine = table_row(p, mine, split);                // row of the combined table
         for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
             bool valid[U];
@@ -528,7 +548,7 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     if (early_idx && (uint32_t)l < min((uint32_t)LPR, nbr_cnt)) first = __ldg(nbr + l);
     float xi[NE];
     if (p.pdl == 1) { pdl_wait(); pdl_launch_dependents(); }
-    if (active) L::load_g(xi, p.Xb + (size_t)(v + (v < bv.split ? p.off_lo : p.off_hi)) * rs, l, p.dim);
+    if (active) L::load_g(xi, p.Xb + (size_t)table_row(p, v, bv.split) * rs, l, p.dim);
     else {
 #pragma unroll
         for (int k = 0; k < NE; k++) xi[k] = 0.f;
@@ -616,7 +636,8 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
 #pragma unroll
             for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(xi[k], acc[k]);   // X[i] += delta (:629-639)
         }
-        const size_t off = (size_t)((uint64_t)v - p.out_base) * rs;
+        // (sharded: out = base of the next table in the flat range, out_base = 0)
+        const size_t off = (size_t)(p.shard_lg ? (uint64_t)shard_row(v, p.shard_lg, p.shard_rows) : (uint64_t)v - p.out_base) * rs;
         // multi-GPU: the exchange is fused here -- the row goes straight into every replica, with one
         // multicast store (NVLS) or one store per peer
         if (p.mc_out != nullptr) {
@@ -669,7 +690,7 @@ __device__ __forceinline__ void stage_negatives(const BatchParams& p, const Batc
     const uint32_t row_bytes = (uint32_t)(rs * sizeof(float));
     for (uint32_t q = threadIdx.x; q < p.s; q += 32) {      // called by warp 0 after expect_tx
         const uint32_t j = __ldg(bv.neg + q);
-        const float* src = p.Xb + (size_t)(j + (j < bv.split ? p.off_lo : p.off_hi)) * rs;
+        const float* src = p.Xb + (size_t)table_row(p, j, bv.split) * rs;
         bulk_g2s(s_neg + (size_t)q * rs, src, row_bytes, bar);
     }
 }
@@ -846,6 +867,27 @@ __global__ void bcast_rows_kernel(const BcastParams b) {
             const float v = __ldcg(b.src + i);
             if (b.mc) mc_st_f32(b.mc + i, v);
             for (uint32_t r = 0; r < b.n_store; r++) __stcg(b.peer[r] + i, v);
+        }
+    }
+}
+
+// Row-sharded tables: move rows [first, first+count) between an identity-layout staging buffer and
+// the flat sharded table.  TO_TABLE: only the rows this rank stores are written (every rank runs
+// the same upload, each fills its own shard); else every row is read (peer loads for remote shards).
+template <bool TO_TABLE>
+__global__ void shard_copy_kernel(float* table, float* staging, uint64_t first, uint64_t count, uint32_t dim,
+                                  uint32_t lg, uint32_t shard_rows, uint32_t rank) {
+    const uint64_t total = count * dim;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint64_t r = i / dim;
+        const uint32_t k = (uint32_t)(i - r * dim);
+        const uint32_t j = (uint32_t)(first + r);
+        const uint32_t row = shard_row(j, lg, shard_rows);
+        if (TO_TABLE) {
+            if (row / shard_rows == rank) table[(size_t)row * dim + k] = staging[i];
+        } else {
+            staging[i] = __ldcg(table + (size_t)row * dim + k);
         }
     }
 }

@@ -168,7 +168,18 @@ int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world);
  *   1. every rank: f2v_comm_peer_export(e, blob)         blob: F2V_PEER_BLOB bytes
  *   2. the caller all-gathers the blobs in rank order (torch.distributed, MPI, a file ...)
  *   3. every rank: f2v_comm_peer_init(e, blobs, rank, world)   world <= 8
- * All ranks must then issue the same sequence of f2v_run_epoch calls.                    */
+ * All ranks must then issue the same sequence of f2v_run_epoch calls.  Where the devices
+ * support it the stores go through an NVLink multicast mapping (one store reaches every
+ * replica; option "multicast" = 0 forces one store per peer).
+ *
+ * Row-sharded tables (option "sharded" = 1 on every rank before the export; power-of-two
+ * world, one process per GPU): instead of a replica per GPU each GPU stores 1/world of the
+ * rows of both tables (VMM allocations mapped by every rank into one flat virtual range; vertex
+ * j lives in shard xorfold(j) mod world).  Gathers of remote rows cross NVLink, a finished row is
+ * stored once, in its shard.  For tables that do not fit one GPU; slower than replicas when
+ * they do.  f2v_set_embeddings (every rank passes the same table, each keeps its rows) must
+ * then be called by all ranks the same number of times; f2v_get_embeddings returns the full
+ * table on every rank; f2v_step is not available.  Results stay bit-identical.            */
 #define F2V_PEER_BLOB 256
 int f2v_comm_peer_export(f2v_engine* e, void* blob);
 int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world);

@@ -45,7 +45,10 @@ def main():
         single.close()
         # peer: NVLink multicast stores where the box supports them; peer_unicast: one store per peer
         # peer_fallback: rank 0 reports that the multicast object cannot be created -> all ranks go unicast
-        for comm in ("peer", "peer_unicast", "peer_fallback", "peer_persistent", "nccl"):
+        # peer_sharded: row-sharded tables (each GPU stores 1/world of the rows, gathers cross NVLink)
+        for comm in ("peer", "peer_unicast", "peer_fallback", "peer_persistent", "peer_sharded", "nccl"):
+            if comm == "peer_sharded" and world & (world - 1):
+                continue
             multi = F.Engine(rp, ci, dim, device=local)
             if comm == "peer_persistent":
                 multi.set_epoch_mode(1)          # one cooperative launch per epoch, exchange barrier inside
@@ -53,6 +56,8 @@ def main():
                 multi.set_option("multicast", 0)
             if comm == "peer_fallback":
                 multi.set_option("multicast", 2)
+            if comm == "peer_sharded":
+                multi.set_option("sharded", 1)
             if comm == "nccl":
                 ids = [F.Engine.comm_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(ids, src=0)
