@@ -302,9 +302,13 @@ static int alloc_tables(f2v_engine* e, uint64_t rows) {
     float* all = nullptr;
     const size_t tbl = sizeof(float) * rows * e->dim;
     CU(cudaMalloc((void**)&all, 2 * tbl));
-    CU(cudaMemset(all, 0, 2 * tbl));
+    // on the engine's stream: it is a non-blocking stream, so a memset on the legacy default stream
+    // would NOT be ordered before the uploads and kernels that follow
+    CU(cudaMemsetAsync(all, 0, 2 * tbl, e->stream));
     if (e->d_Xall) {
-        CU(cudaMemcpy(all + (size_t)e->cur * rows * e->dim, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpyAsync(all + (size_t)e->cur * rows * e->dim, e->d_X[e->cur], sizeof(float) * e->n * e->dim,
+                           cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
         CU(cudaFree(e->d_Xall));
     }
     e->d_Xall = all;
@@ -345,8 +349,8 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
     // plans are (re)built rarely; a synchronous copy keeps the host vectors' lifetime simple
     CU(cudaStreamSynchronize(e->stream));
     if (total) {
-        CU(cudaMemcpy(pl.d_items, items.data(), sizeof(Item) * total, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(pl.d_hub, hub.data(), sizeof(HubInfo) * total, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(pl.d_items, items.data(), sizeof(Item) * total, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(pl.d_hub, hub.data(), sizeof(HubInfo) * total, cudaMemcpyHostToDevice, e->stream));
     }
     if (pl.cap_ptr < nb + 1 || !pl.d_item_ptr) {
         if (pl.d_item_ptr) CU(cudaFree(pl.d_item_ptr));
@@ -354,7 +358,10 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         CU(cudaMalloc((void**)&pl.d_item_ptr, sizeof(uint64_t) * (nb + 1)));
         pl.cap_ptr = nb + 1;
     }
-    CU(cudaMemcpy(pl.d_item_ptr, item_ptr.data(), sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(pl.d_item_ptr, item_ptr.data(), sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice, e->stream));
+    // on the engine's (non-blocking) stream, and finished before the host vectors go away: a copy on
+    // the legacy stream would not be ordered before the launches that read the plan
+    CU(cudaStreamSynchronize(e->stream));
     if (max_slots > e->slots_cap || !e->d_partials) {
         if (e->d_partials) CU(cudaFree(e->d_partials));
         if (e->d_counters) CU(cudaFree(e->d_counters));
@@ -362,7 +369,7 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         uint64_t slots = std::max<uint64_t>(max_slots, 1);
         CU(cudaMalloc((void**)&e->d_partials, sizeof(float) * slots * e->dim));
         CU(cudaMalloc((void**)&e->d_counters, sizeof(uint32_t) * slots));
-        CU(cudaMemset(e->d_counters, 0, sizeof(uint32_t) * slots));
+        CU(cudaMemsetAsync(e->d_counters, 0, sizeof(uint32_t) * slots, e->stream));
         e->slots_cap = slots;
     }
     pl.batch = batch; pl.chunk = chunk; pl.par = par; pl.walk = walk; pl.rank = rank; pl.world = world;
@@ -648,8 +655,9 @@ int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz, const 
     CU(cudaEventCreate(&e->ev1));
     CU(cudaMalloc((void**)&e->d_rowptr, sizeof(uint64_t) * (n + 1)));
     CU(cudaMalloc((void**)&e->d_colids, sizeof(uint32_t) * (nnz ? nnz : 1)));
-    CU(cudaMemcpy(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice));
-    if (nnz) CU(cudaMemcpy(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, e->stream));
+    if (nnz) CU(cudaMemcpyAsync(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     e->rows_alloc = n;                       // tables are allocated on first use (ensure_tables): a row-sharded
                                              // engine never holds a full-size table
     CU(cudaMalloc((void**)&e->d_lut, sizeof(float) * kLutAlloc));
@@ -990,7 +998,9 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         p.lo = b * batch;
         p.split = (uint32_t)(b * batch);
         p.neg = e->d_neg + e->neg_off + b * W;
-        p.pdl = (e->pdl && e->world == 1) ? ((b >= 1 && nb >= 2 && e->pdl >= 2) ? 2 : 1) : 0;
+        // the epoch's first launch is an ordinary one: it follows host copies (negatives, walks, the
+        // table) and must see a freshly invalidated L1; launches 1.. are programmatic dependents
+        p.pdl = (e->pdl && e->world == 1 && b >= 1) ? (e->pdl >= 2 ? 2 : 1) : 0;
         if (e->peer_mode) {
             // minibatch b reads rows its peers stored during step_id (minibatch b-1); it publishes step_id+1
             p.wait_step = (e->peer_debug & 2) ? 0 : e->step_id;
@@ -1200,9 +1210,10 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
     CU(cudaStreamSynchronize(e->stream));
     if (!e->d_flags) {
         CU(cudaMalloc((void**)&e->d_flags, sizeof(uint64_t) * kMaxWorld * kFlagStride));
-        CU(cudaMemset(e->d_flags, 0, sizeof(uint64_t) * kMaxWorld * kFlagStride));
+        CU(cudaMemsetAsync(e->d_flags, 0, sizeof(uint64_t) * kMaxWorld * kFlagStride, e->stream));
         CU(cudaMalloc((void**)&e->d_done, sizeof(uint32_t) * 32));
-        CU(cudaMemset(e->d_done, 0, sizeof(uint32_t) * 32));
+        CU(cudaMemsetAsync(e->d_done, 0, sizeof(uint32_t) * 32, e->stream));
+        CU(cudaStreamSynchronize(e->stream));        // peers may store into the flag page as soon as it is exported
     }
     PeerBlob b;
     memset(&b, 0, sizeof(b));
@@ -1356,8 +1367,9 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
     DRV(g_drv.MemMap(mcva, size, 0, mc, 0));
     DRV(g_drv.MemSetAccess(mcva, size, &ad, 1));
     // move the live state over (through the unicast mapping) and drop the cudaMalloc'ed tables
-    CU(cudaMemset((void*)uc, 0, size));
-    CU(cudaMemcpy((void*)uc, e->d_Xall, 2 * tbl, cudaMemcpyDeviceToDevice));
+    CU(cudaMemsetAsync((void*)uc, 0, size, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpyAsync((void*)uc, e->d_Xall, 2 * tbl, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaDeviceSynchronize());
     CU(cudaFree(e->d_Xall));
     CU(cudaFree(e->d_flags));
@@ -1492,7 +1504,8 @@ static int shard_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world
     ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = e->device; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
     DRV(g_drv.MemSetAccess(va, total, &ad, 1));
     // zero this rank's shard, then move any live state over (only the rows this rank stores)
-    for (int t = 0; t < 2; t++) CU(cudaMemset((void*)(va + ((size_t)t * world + rank) * shard_bytes), 0, shard_bytes));
+    for (int t = 0; t < 2; t++)
+        CU(cudaMemsetAsync((void*)(va + ((size_t)t * world + rank) * shard_bytes), 0, shard_bytes, e->stream));
     float* old_all = e->d_Xall;
     float* old_live = e->d_Xall ? e->d_X[e->cur] : nullptr;
     e->shard_va = va; e->shard_bytes = shard_bytes; e->shard_lg = lg; e->shard_rows = (uint32_t)rows;

@@ -112,15 +112,19 @@ __device__ __forceinline__ BatchVar batch_var(const BatchParams& p) {
     return BatchVar{p.items, p.hub, p.n_items, p.split, (uint32_t)p.lo, p.neg};
 }
 
-// Vertex id -> row of a table.  Sharded: shard(j) * shard_rows + (j >> lg), where shard(j) is the
-// XOR of all lg-bit digits of j: a bijection between the low digit and the shard for any fixed
-// high part (so (shard, j >> lg) is unique), and unlike j mod W it spreads R-MAT's hubs -- ids with
-// few one-bits, nearly all congruent 0 mod W -- over the GPUs.
+// Vertex id -> row of a table.  Sharded: shard(j) * shard_rows + (j >> lg) with
+// shard(j) = (low digit of j) XOR hash(j >> lg): for any fixed high part the low digit maps onto
+// the shards one-to-one (so (shard, j >> lg) is a dense unique row), and unlike j mod W it spreads
+// R-MAT's hubs -- ids with few one-bits, nearly all congruent 0 mod W -- over the GPUs.
+// Branch-free; lg = 0 (not sharded) gives row = j.
 __host__ __device__ __forceinline__ uint32_t shard_row(uint32_t j, uint32_t lg, uint32_t shard_rows) {
-    if (lg == 0) return j;
-    uint32_t f = j;
-    for (uint32_t s = lg; s < 32; s += lg) f ^= j >> s;
-    return (f & ((1u << lg) - 1u)) * shard_rows + (j >> lg);
+    const uint32_t h = j >> lg;
+#ifdef __CUDA_ARCH__
+    const uint32_t mix = __umulhi(h, 0x9E3779B1u);
+#else
+    const uint32_t mix = (uint32_t)(((uint64_t)h * 0x9E3779B1ull) >> 32);
+#endif
+    return ((j ^ mix) & ((1u << lg) - 1u)) * shard_rows + h;
 }
 // Row of the combined (both tables) range that holds vertex j for a launch with the given split.
 __device__ __forceinline__ uint32_t table_row(const BatchParams& p, uint32_t j, uint32_t split) {
@@ -468,7 +472,9 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     for (uint32_t base = 0; base < cnt_max; base += LPR) {
         const uint32_t nb = cnt > base ? min((uint32_t)LPR, cnt - base) : 0u;
         const uint32_t nb_max = min((uint32_t)LPR, cnt_max - base);
-        uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldg(idx + base + l) : self);
+        // (ld.global.cg, not the non-coherent path: negative and walk indices are rewritten between
+        // epochs, and with dependent launches an SM's L1 can outlive a launch boundary)
+        uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldcg(idx + base + l) : self);
         mine = table_row(p, mine, split);                // row of the combined table
         for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
@@ -636,8 +642,8 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
 #pragma unroll
             for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(xi[k], acc[k]);   // X[i] += delta (:629-639)
         }
-        // (sharded: out = base of the next table in the flat range, out_base = 0)
-        const size_t off = (size_t)(p.shard_lg ? (uint64_t)shard_row(v, p.shard_lg, p.shard_rows) : (uint64_t)v - p.out_base) * rs;
+        // (out_base > 0 only for the teacher-forced single step, which is never sharded)
+        const size_t off = (size_t)((uint64_t)shard_row(v, p.shard_lg, p.shard_rows) - p.out_base) * rs;
         // multi-GPU: the exchange is fused here -- the row goes straight into every replica, with one
         // multicast store (NVLS) or one store per peer
         if (p.mc_out != nullptr) {
@@ -689,7 +695,7 @@ __device__ __forceinline__ void stage_negatives(const BatchParams& p, const Batc
     const size_t rs = L::stride(p.dim);
     const uint32_t row_bytes = (uint32_t)(rs * sizeof(float));
     for (uint32_t q = threadIdx.x; q < p.s; q += 32) {      // called by warp 0 after expect_tx
-        const uint32_t j = __ldg(bv.neg + q);
+        const uint32_t j = __ldcg(bv.neg + q);
         const float* src = p.Xb + (size_t)table_row(p, j, bv.split) * rs;
         bulk_g2s(s_neg + (size_t)q * rs, src, row_bytes, bar);
     }

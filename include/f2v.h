@@ -175,7 +175,7 @@ int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world);
  * Row-sharded tables (option "sharded" = 1 on every rank before the export; power-of-two
  * world, one process per GPU): instead of a replica per GPU each GPU stores 1/world of the
  * rows of both tables (VMM allocations mapped by every rank into one flat virtual range; vertex
- * j lives in shard xorfold(j) mod world).  Gathers of remote rows cross NVLink, a finished row is
+ * j lives in shard (j xor hash(j / world)) mod world).  Gathers of remote rows cross NVLink, a finished row is
  * stored once, in its shard.  For tables that do not fit one GPU; slower than replicas when
  * they do.  f2v_set_embeddings (every rank passes the same table, each keeps its rows) must
  * then be called by all ranks the same number of times; f2v_get_embeddings returns the full
