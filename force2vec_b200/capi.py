@@ -15,7 +15,7 @@ ENGINE_SYMBOLS = [
     "f2v_set_walks",
     "f2v_get_walks", "f2v_sample_walks", "f2v_step", "f2v_run_epoch", "f2v_run_epoch_host",
     "f2v_set_epoch_mode", "f2v_set_option", "f2v_launch_count", "f2v_last_epoch_ms", "f2v_comm_unique_id",
-    "f2v_comm_init", "f2v_comm_peer_export", "f2v_comm_peer_init", "f2v_trace_ms",
+    "f2v_comm_init", "f2v_comm_peer_export", "f2v_comm_peer_init", "f2v_trace_ms", "f2v_shard_row",
 ]
 HOST_SYMBOLS = [
     "f2v_rng_create", "f2v_rng_destroy", "f2v_rng_next", "f2v_init_embeddings", "f2v_build_lut",
@@ -81,6 +81,8 @@ def lib():
     L.f2v_comm_unique_id.argtypes = [vp]
     L.f2v_comm_init.argtypes = [vp, vp, i32, i32]
     L.f2v_trace_ms.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.f2v_shard_row.argtypes = [u32, u32, u32]
+    L.f2v_shard_row.restype = u32
     L.f2v_comm_peer_export.argtypes = [vp, vp]
     L.f2v_comm_peer_init.argtypes = [vp, vp, i32, i32]
     # host side

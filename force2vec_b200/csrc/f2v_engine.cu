@@ -1167,6 +1167,10 @@ int f2v_last_epoch_ms(f2v_engine* e, float* ms) {
     return F2V_OK;
 }
 
+uint32_t f2v_shard_row(uint32_t vertex, uint32_t log2_world, uint32_t shard_rows) {
+    return shard_row(vertex, log2_world, shard_rows);
+}
+
 int f2v_trace_ms(f2v_engine* e, float* ms, uint32_t cap, uint32_t* count) {
     if (!e || !ms || !count) return fail(F2V_ERR_ARG, "null argument");
     if (!e->trace || e->trace_n == 0) return fail(F2V_ERR_STATE, "no traced epoch (f2v_set_option trace 1, epoch mode 0)");

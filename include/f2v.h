@@ -180,6 +180,9 @@ int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world);
  * they do.  f2v_set_embeddings (every rank passes the same table, each keeps its rows) must
  * then be called by all ranks the same number of times; f2v_get_embeddings returns the full
  * table on every rank; f2v_step is not available.  Results stay bit-identical.            */
+/* Row of a sharded table that holds `vertex` (the placement function of the row-sharded mode:
+ * shard = row / shard_rows).  Exposed for tests.                                          */
+uint32_t f2v_shard_row(uint32_t vertex, uint32_t log2_world, uint32_t shard_rows);
 #define F2V_PEER_BLOB 256
 int f2v_comm_peer_export(f2v_engine* e, void* blob);
 int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world);

@@ -247,3 +247,24 @@ def test_cli_without_gpu_exits_nonzero():
     assert r.returncode == 1 and b"engine error" in r.stderr
     r = subprocess.run([exe], capture_output=True, cwd="/tmp")
     assert r.returncode == 1 and b"Valid input file needed" in r.stdout
+
+
+@pytest.mark.parametrize("lg", [0, 1, 2, 3])
+def test_shard_row_is_a_dense_bijection_that_spreads_hubs(lg):
+    """Placement of the row-sharded mode: vertex -> (shard, local row) must be one-to-one with
+    local row = vertex >> lg (dense), the identity for one GPU, and must not put R-MAT's hubs
+    (ids with few one-bits) on one GPU the way `vertex mod world` does."""
+    L = F.lib()
+    world, n = 1 << lg, 1 << 16
+    rows = n >> lg
+    r = np.array([L.f2v_shard_row(j, lg, rows) for j in range(n)], np.int64)
+    assert len(np.unique(r)) == n and r.min() == 0 and r.max() == n - 1          # bijection onto [0, n)
+    assert np.array_equal(r % rows, np.arange(n) >> lg)                           # local row = j >> lg
+    if lg == 0:
+        assert np.array_equal(r, np.arange(n))
+        return
+    shard = r // rows
+    assert np.bincount(shard, minlength=world).tolist() == [rows] * world
+    hubs = np.array([0] + [1 << k for k in range(16)] + [(1 << a) | (1 << b) for a in range(16) for b in range(a)])
+    cnt = np.bincount(shard[hubs], minlength=world)
+    assert cnt.max() <= 2.0 * len(hubs) / world, cnt                              # vs j mod world: almost all on shard 0
