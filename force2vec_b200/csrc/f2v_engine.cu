@@ -418,7 +418,10 @@ static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_
 
 template <class L, int MODEL>
 static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
-    return persist ? launch_batch_k<L, MODEL, true>(p, st, sm_count) : launch_batch_k<L, MODEL, false>(p, st, sm_count);
+    // (the per-minibatch kernel with persistent CTAs was measured slower and is no longer instantiated;
+    // the persistent variant that remains is the one-launch-per-epoch kernel, epoch mode 1)
+    (void)persist;
+    return launch_batch_k<L, MODEL, false>(p, st, sm_count);
 }
 
 template <class L>
@@ -441,11 +444,7 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         // (batch 16384, option 7: 2.82 / 1.90 / 2.09 ms for the three layouts; batch 4096: 5.76 / 6.72 / 7.03)
         switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u && model == kWalk ? 4 : (p.n_items >= 8000u ? 1 : 0))) {
         case 1: return launch_batch_m<VecL<64, 8, 2, 4>>(model, p, st, sm_count, persist);
-        case 2: return launch_batch_m<VecL<64, 16, 4, 4>>(model, p, st, sm_count, persist);
-        case 3: return launch_batch_m<VecL<64, 16, 2, 5>>(model, p, st, sm_count, persist);
         case 4: return launch_batch_m<VecL<64, 8, 2, 5>>(model, p, st, sm_count, persist);
-        case 5: return launch_batch_m<VecL<64, 16, 4, 5>>(model, p, st, sm_count, persist);
-        case 6: return launch_batch_m<VecL<64, 8, 4, 3>>(model, p, st, sm_count, persist);
         default: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count, persist);
         }
     case 128:
@@ -454,18 +453,9 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         // slower below); small launches are latency-bound, not occupancy-bound, and run 8 rows in
         // flight per group at 128 registers (5-11 % faster below ~12 K items)
         switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u ? 8 : (p.n_items < 12000u ? 11 : 3))) {
-        case 1: return launch_batch_m<VecL<128, 32, 8, 2>>(model, p, st, sm_count, persist);
-        case 2: return launch_batch_m<VecL<128, 8, 2, 2>>(model, p, st, sm_count, persist);
         case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count, persist);
-        case 4: return launch_batch_m<VecL<128, 8, 2, 3>>(model, p, st, sm_count, persist);
-        case 5: return launch_batch_m<VecL<128, 8, 1, 3>>(model, p, st, sm_count, persist);
-        case 6: return launch_batch_m<VecL<128, 16, 4, 2>>(model, p, st, sm_count, persist);
-        case 7: return launch_batch_m<VecL<128, 8, 1, 4>>(model, p, st, sm_count, persist);
         case 8: return launch_batch_m<VecL<128, 16, 2, 5>>(model, p, st, sm_count, persist);
-        case 9: return launch_batch_m<VecL<128, 16, 2, 6>>(model, p, st, sm_count, persist);
-        case 10: return launch_batch_m<VecL<128, 16, 2, 7>>(model, p, st, sm_count, persist);
         case 11: return launch_batch_m<VecL<128, 16, 8, 2>>(model, p, st, sm_count, persist);
-        case 12: return launch_batch_m<VecL<128, 8, 8, 2>>(model, p, st, sm_count, persist);
         default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st, sm_count, persist);   // 3
         }
     case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st, sm_count, persist);
@@ -1142,7 +1132,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "neg_smem")) e->neg_smem = value != 0;
     else if (!strcmp(name, "par")) e->par = (int)value;
     else if (!strcmp(name, "prefetch")) { (void)value; }   // L2 prefetch variants were measured (no gain) and removed
-    else if (!strcmp(name, "persist")) e->persist = value != 0;
+    else if (!strcmp(name, "persist")) { (void)value; }    // removed: see launch_batch_t
     else if (!strcmp(name, "peer_debug")) e->peer_debug = (int)value;
     else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;
     else if (!strcmp(name, "pdl")) e->pdl = (int)value;

@@ -130,12 +130,21 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
 /* Execution mode of f2v_run_epoch: 0 = one kernel launch per minibatch (default),
  * 1 = one persistent cooperative kernel per epoch with a grid barrier per minibatch.  */
 int f2v_set_epoch_mode(f2v_engine* e, int mode);
-/* Tuning knobs (integers): "variant" = lane layout of the d=128 kernels (-1 default = auto: 16
- * lanes per row, 2 rows in flight per group, 4 CTAs/SM at 64 registers, or 5 CTAs/SM at 48
- * registers for launches with >= 48 K items; 3 / 8 force one of the two; 0: 16x4; 1: 32x8; 2: 8x2;
- * ...), "neg_smem"
- * = 0 disables the TMA staging of shared negatives (they are then gathered from L2 like bs=1
- * negatives), "par" = lane groups a minibatch should fill (adaptive chunk length, 0 = fixed). */
+/* Tuning knobs (integers; defaults are the measured optimum, profiles/r1_tune_v5.md):
+ *   "variant"   lane layout of the d=128 / d=64 kernels; -1 (default) = by launch size.  d=128:
+ *               3 = 16 lanes per row, 2 rows in flight per group, 4 CTAs/SM at 64 registers;
+ *               8 = the same at 5 CTAs/SM and 48 registers (launches with >= 48 K items);
+ *               11 = 8 rows in flight at 128 registers (launches with < 12 K items); 0 = 4 rows in
+ *               flight, 3 CTAs/SM.  d=64: 0 = 4 rows in flight, 1 = 2 rows in flight at 4 CTAs/SM,
+ *               4 = at 5 CTAs/SM.
+ *   "neg_smem"  0 disables the TMA staging of shared negatives (gathered from L2 instead)
+ *   "par"       lane groups a minibatch should fill (adaptive chunk length, 0 = fixed chunk)
+ *   "min_chunk" lower bound of the adaptive chunk length (0 = default: 16 for batches <= 8192, else 8)
+ *   "pdl"       programmatic dependent launch of consecutive minibatches: 0 off, 1, 2 (default)
+ *   "multicast" peer exchange through NVLink multicast stores: 1 (default) when supported, 0 never
+ *   "sharded"   1 = row-sharded tables (set on every rank before f2v_comm_peer_export)
+ *   "trace"     1 = record per-minibatch times (f2v_trace_ms)
+ *   "order", "peer_sig", "peer_debug", "epoch_ctas"  development probes (tools/mgpu_probe.py)  */
 int f2v_set_option(f2v_engine* e, const char* name, int64_t value);
 /* Kernel launches issued by this engine since creation (force + sampler kernels).     */
 uint64_t f2v_launch_count(const f2v_engine* e);

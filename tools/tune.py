@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tools/tune.py -- sweep engine knobs on one resident workload (development aid, not the bench).
-   python tools/tune.py --scale 20 --model 6 --dim 128 --batches 16384,65536 --variants 0,1,2,3 --chunks 64,128"""
+   python tools/tune.py --scale 20 --model 6 --dim 128 --batches 16384,65536 --variants 3,8,11 --chunks 64,128"""
 import argparse
 import itertools
 import json
