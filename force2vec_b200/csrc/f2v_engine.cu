@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
 #include <new>
 #include <string>
 #include <unistd.h>
@@ -52,7 +53,9 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
+static std::mutex g_load_mutex;           // engines of one process may be driven by several threads
 static int nccl_load() {
+    std::lock_guard<std::mutex> lock(g_load_mutex);
     if (g_nccl.handle) return F2V_OK;
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -101,6 +104,7 @@ struct DrvApi {
 };
 static DrvApi g_drv;
 static int drv_load() {
+    std::lock_guard<std::mutex> lock(g_load_mutex);
     if (g_drv.loaded) return F2V_OK;
     struct { const char* name; void** slot; } tab[] = {
         {"cuGetErrorString", (void**)&g_drv.GetErrorString}, {"cuDeviceGet", (void**)&g_drv.DeviceGet},
@@ -264,7 +268,7 @@ struct f2v_engine {
     int peer_debug = 0;                      // timing probes only: 1 = no peer row stores, 2 = no flag barrier
     int order = -1;                          // item order after the hub chunks: 0 descending degree, 1 light rows first,
                                              // 2 light rows interleaved; -1 = default (0 on one GPU, 1 on several)
-    int pdl = 2;                             // programmatic dependent launch of consecutive minibatches (single GPU)
+    int pdl = 2;                             // programmatic dependent launch of consecutive minibatches (0 off, 1, 2)
     int peer_sig = 1;                        // 1: a 1-CTA kernel after the force kernel publishes the step (default);
                                              // 0: the force kernel's last CTA does (a system fence per CTA: measured slower)
 };

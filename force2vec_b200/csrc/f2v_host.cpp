@@ -8,7 +8,11 @@
 #include "f2v_plan.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -467,6 +471,100 @@ extern "C" int f2v_train(const f2v_train_args* a, float* X_out, double* seconds)
     return F2V_OK;
 }
 
+// ------------------------------------------------------------------ multi-GPU driver ----
+// The same run on `gpus` devices of this node from ONE process: one host thread and one engine per
+// device, replicated tables, the fused peer-store exchange (engines of one process reach each
+// other's tables by plain peer access).  Thread 0 owns the libc-compatible stream and draws the
+// walks / negatives of every epoch into host buffers all threads upload from, so the result is the
+// single-GPU result bit for bit (for equal `chunk`).
+namespace {
+struct SpinBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0, gen = 0, parties;
+    explicit SpinBarrier(int n) : parties(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == parties) { count = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+}  // namespace
+
+extern "C" int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, double* seconds) {
+    if (gpus <= 1) return f2v_train(a, X_out, seconds);
+    if (!a || !X_out || !a->rowptr) return F2V_ERR_ARG;
+    if (a->option != F2V_TDIST && a->option != F2V_SIGMOID && a->option != F2V_WALK) return F2V_ERR_ARG;
+    if (gpus > 8 || gpus > f2v_device_count()) return F2V_ERR_ARG;
+    const int model = a->option;
+    const int bs = model == F2V_WALK ? 0 : (a->bs ? 1 : 0);
+    const int G = gpus;
+    auto t0 = std::chrono::steady_clock::now();
+    f2v_rng* g = f2v_rng_create(a->seed);
+    if (!g) return F2V_ERR_NOMEM;
+    f2v_init_embeddings(g, model, a->n, a->dim, X_out);
+    float lut[F2V_LUT_SIZE];
+    f2v_build_lut(lut);
+    const uint64_t slen = f2v_neg_stream_len(model, a->n, a->batch, a->nsamples, bs);
+    std::vector<uint32_t> neg(slen ? slen : 1);
+    const bool host_walks = model == F2V_WALK && a->walk_sampler == 0;
+    std::vector<uint32_t> walks(host_walks ? a->n * (uint64_t)F2V_WALKLEN : 1);
+    std::vector<char> blobs((size_t)G * F2V_PEER_BLOB);
+    std::vector<int> status(G, F2V_OK);
+    std::vector<std::string> errs(G);
+    SpinBarrier bar(G);
+    std::atomic<int> failed{0};
+    auto worker = [&](int r) {
+        f2v_engine* e = nullptr;
+        int rc = F2V_OK;
+        auto step = [&](int code) {          // record the first error of this thread; all threads meet at the
+            if (code && !rc) { rc = code; errs[r] = f2v_last_error(); failed.store(1); }   // next barrier and stop together
+        };
+        step(f2v_create(&e, a->device + r, a->n, a->nnz, a->rowptr, a->colids, a->dim));
+        if (!rc && a->epoch_mode) step(f2v_set_epoch_mode(e, a->epoch_mode));
+        if (!rc) step(f2v_comm_peer_export(e, blobs.data() + (size_t)r * F2V_PEER_BLOB));
+        bar.wait();
+        if (!failed.load()) step(f2v_comm_peer_init(e, blobs.data(), r, G));
+        bar.wait();
+        if (!failed.load()) {
+            if (model != F2V_TDIST) step(f2v_set_lut(e, lut, F2V_LUT_SIZE));
+            step(f2v_set_embeddings(e, X_out));
+        }
+        bar.wait();
+        for (uint32_t it = 0; it < a->iterations && !failed.load(); it++) {
+            if (r == 0) {                    // the serial draws of this epoch (reference order: walks, then negatives)
+                if (host_walks) step(f2v_draw_walks(g, a->n, a->nnz, a->rowptr, a->colids, walks.data()));
+                step(f2v_draw_epoch_negatives(g, model, a->n, a->batch, a->nsamples, bs, neg.data()));
+            }
+            bar.wait();
+            if (failed.load()) break;
+            if (model == F2V_WALK) step(host_walks ? f2v_set_walks(e, walks.data()) : f2v_sample_walks(e, a->seed, it));
+            step(f2v_set_negatives(e, neg.data(), slen));
+            if (!rc) step(f2v_sync(e));      // the host buffers are redrawn by thread 0 after the next barrier
+            bar.wait();
+            if (failed.load()) break;        // nobody has launched this epoch yet: safe to stop together
+            step(f2v_run_epoch(e, model, a->batch, a->nsamples, bs, a->lr, a->chunk));
+        }
+        if (e && !rc) step(f2v_sync(e));
+        bar.wait();
+        if (r == 0 && !failed.load()) step(f2v_get_embeddings(e, X_out));
+        bar.wait();                          // nobody unmaps a table a peer may still be storing into
+        if (e) f2v_destroy(e);
+        status[r] = rc;
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < G; r++) th.emplace_back(worker, r);
+    worker(0);
+    for (auto& t : th) t.join();
+    f2v_rng_destroy(g);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    for (int r = 0; r < G; r++)
+        if (status[r]) { fprintf(stderr, "f2v_train_gpus: device %d: %s\n", a->device + r, errs[r].c_str()); return status[r]; }
+    return F2V_OK;
+}
+
 // ------------------------------------------------------------------ C++ mirror ---------
 namespace f2v {
 
@@ -504,7 +602,7 @@ std::vector<float> algorithms::run(int option, int bs, uint32_t iters, uint32_t 
     a.dim = DIM; a.option = option; a.bs = bs; a.iterations = iters; a.batch = batch; a.nsamples = ns;
     a.lr = lr; a.seed = seed; a.device = device; a.walk_sampler = walk_sampler; a.epoch_mode = epoch_mode;
     double sec = 0;
-    int rc = f2v_train(&a, nCoordinates.data(), &sec);
+    int rc = gpus > 1 ? f2v_train_gpus(&a, gpus, nCoordinates.data(), &sec) : f2v_train(&a, nCoordinates.data(), &sec);
     if (rc != F2V_OK) {
         // the reference's error convention: message + exit(1) (Test/Force2Vec.cpp:119,186)
         fprintf(stderr, "Force2Vec GPU engine error %d: %s\n", rc, f2v_last_error());

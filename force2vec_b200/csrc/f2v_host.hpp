@@ -29,7 +29,8 @@ public:
     uint32_t DIM;
     std::string filename;
     std::string outputdir;
-    int device = 0;                    // CUDA device (no reference counterpart)
+    int device = 0;                    // (first) CUDA device (no reference counterpart)
+    int gpus = 1;                      // > 1: devices device..device+gpus-1, minibatches split across them
     int epoch_mode = 0;                // engine execution mode (include/f2v.h f2v_set_epoch_mode)
     int walk_sampler = 0;              // 0 = libc-stream host walks, 1 = device sampler
     uint32_t seed = 1;                 // Test/Force2Vec.cpp:126 srand(1)

@@ -168,6 +168,7 @@ class Algorithms:
         self.walk_sampler = 0
         self.seed = 1
         self.chunk = 0
+        self.gpus = 1
         self.nCoordinates = np.zeros((self.rows, self.DIM), np.float32)
 
     def _run(self, option, bs, iterations, batch, ns, lr, tag, write):
@@ -179,7 +180,10 @@ class Algorithms:
         a.iterations, a.batch, a.nsamples, a.lr = iterations, batch, ns, lr
         a.seed, a.device, a.walk_sampler, a.epoch_mode, a.chunk = self.seed, self.device, self.walk_sampler, self.epoch_mode, self.chunk
         sec = C.c_double()
-        check(lib().f2v_train(C.byref(a), _p(self.nCoordinates), C.byref(sec)), "f2v_train")
+        if self.gpus > 1:
+            check(lib().f2v_train_gpus(C.byref(a), self.gpus, _p(self.nCoordinates), C.byref(sec)), "f2v_train_gpus")
+        else:
+            check(lib().f2v_train(C.byref(a), _p(self.nCoordinates), C.byref(sec)), "f2v_train")
         if write:
             self.writeToFile("%s%dD%dIT%dNS%d" % (tag, batch, self.DIM, iterations, ns))
         return [sec.value]
