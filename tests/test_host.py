@@ -268,3 +268,15 @@ def test_shard_row_is_a_dense_bijection_that_spreads_hubs(lg):
     hubs = np.array([0] + [1 << k for k in range(16)] + [(1 << a) | (1 << b) for a in range(16) for b in range(a)])
     cnt = np.bincount(shard[hubs], minlength=world)
     assert cnt.max() <= 2.0 * len(hubs) / world, cnt                              # vs j mod world: almost all on shard 0
+
+
+def test_multi_gpu_driver_without_gpus_fails_loudly():
+    """f2v_train_gpus asks for more devices than exist (none here): an error, never a CPU fallback."""
+    if F.lib().f2v_device_count() >= 2:
+        pytest.skip("two GPUs are present")
+    from force2vec_b200 import capi
+    rp, ci = host.rmat_csr(6, 4, 1)
+    alg = F.Algorithms(rp, ci, "g.mtx", "/tmp/", 16)
+    alg.gpus = 2
+    with pytest.raises(capi.F2VError):
+        alg.AlgoForce2VecNS(1, 0, 16, 5, 0.02, write=False)
