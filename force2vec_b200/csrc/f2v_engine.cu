@@ -262,6 +262,8 @@ struct f2v_engine {
     CUdeviceptr shard_va = 0;
     size_t shard_bytes = 0;                  // bytes of one shard of one table
     float* d_shard_stage = nullptr;          // staging chunk for host <-> sharded table copies
+    int exchange_timeout_ms = 30000;         // option "exchange_timeout_ms": a peer that never publishes its step
+                                             // is reported as an error instead of hanging the launch (0 = wait for ever)
     int trace = 0;                           // option "trace": one CUDA event per minibatch of the last epoch
     std::vector<cudaEvent_t> trace_ev;
     uint64_t trace_n = 0;
@@ -555,6 +557,7 @@ static int shard_copy(f2v_engine* e, bool to_table, uint64_t first, uint64_t cou
         p.n_peers = (uint32_t)(e->world - 1);
         p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
         p.flags = e->d_flags; p.done = e->d_done;
+        p.timeout_ns = (uint64_t)e->exchange_timeout_ms * 1000000ull; p.timed_out = e->d_done + 1;
         p.wait_step = e->step_id;
         peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
         CU(cudaGetLastError());
@@ -728,11 +731,22 @@ int f2v_set_stream(f2v_engine* e, void* cuda_stream) {
     return F2V_OK;
 }
 
+// Multi-GPU: did a launch give up waiting for a peer's exchange step?  (stream already synchronised)
+static int check_exchange(f2v_engine* e) {
+    if (!e->peer_mode || !e->d_done) return F2V_OK;
+    uint32_t flag = 0;
+    CU(cudaMemcpy(&flag, e->d_done + 1, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag)
+        return fail(F2V_ERR_STATE, "multi-GPU exchange timed out after %d ms: a peer rank did not publish its step "
+                                   "(did every rank issue the same calls?); the tables are not valid", e->exchange_timeout_ms);
+    return F2V_OK;
+}
+
 int f2v_sync(f2v_engine* e) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    return F2V_OK;
+    return check_exchange(e);
 }
 
 int f2v_set_embeddings(f2v_engine* e, const float* X) {
@@ -754,11 +768,14 @@ int f2v_set_embeddings(f2v_engine* e, const float* X) {
 int f2v_get_embeddings(f2v_engine* e, float* X) {
     if (!e || !X) return fail(F2V_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
-    if (e->shard_mode) return shard_copy(e, false, 0, e->n, X);     // remote shards are read over NVLink
+    if (e->shard_mode) {                                             // remote shards are read over NVLink
+        int r = shard_copy(e, false, 0, e->n, X);
+        return r ? r : check_exchange(e);
+    }
     { int r = ensure_tables(e); if (r) return r; }
     CU(cudaMemcpyAsync(X, e->d_X[e->cur], sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    return F2V_OK;
+    return check_exchange(e);
 }
 
 int f2v_get_rows(f2v_engine* e, uint64_t first_row, uint64_t nrows, float* rows) {
@@ -946,6 +963,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         }
         p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
         p.flags = e->d_flags; p.done = e->d_done;
+        p.timeout_ns = (uint64_t)e->exchange_timeout_ms * 1000000ull; p.timed_out = e->d_done + 1;
         for (int r = 0, k = 0; r < e->world && !e->mc_mode; r++) {
             if (r == e->rank) continue;
             p.peer_out[k] = e->shard_mode ? nullptr : e->peerX[r][1 - e->cur];
@@ -1069,7 +1087,7 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
         if (r) return r;
         CU(cudaStreamSynchronize(e->stream));
         if (X_out) { r = f2v_get_embeddings(e, X_out); if (r) return r; }
-        return F2V_OK;
+        return check_exchange(e);
     }
     { r = ensure_tables(e); if (r) return r; }
     // multi-GPU with the peer exchange: rank r moves only rows [lo, hi) = its 1/world share of the
@@ -1120,7 +1138,7 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
                            cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (overlap) CU(cudaStreamSynchronize(e->copy_stream));
-    return F2V_OK;
+    return check_exchange(e);
 }
 
 int f2v_set_epoch_mode(f2v_engine* e, int mode) {
@@ -1143,6 +1161,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "order")) e->order = (int)value;
     else if (!strcmp(name, "multicast")) e->want_mc = (int)value;
     else if (!strcmp(name, "trace")) e->trace = (int)value;
+    else if (!strcmp(name, "exchange_timeout_ms")) e->exchange_timeout_ms = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "sharded")) e->want_shard = value != 0;
     else if (!strcmp(name, "epoch_ctas")) g_epoch_ctas_per_sm = (int)value;
     else if (!strcmp(name, "min_chunk")) { min_chunk_override() = (uint32_t)std::max<int64_t>(0, value); e->epoch_plan.batch = 0; e->step_plan.batch = 0; }

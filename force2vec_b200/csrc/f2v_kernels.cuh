@@ -92,6 +92,11 @@ struct BatchParams {
     // `mc_flag` the multicast mapping of this rank's exchange flag.  nullptr = unicast peer stores.
     float* mc_out;
     uint64_t* mc_flag;
+    // A rank that never publishes its step (it failed, or was never launched) must not hang its
+    // peers for ever: a wait longer than timeout_ns sets *timed_out and the launch carries on (its
+    // results are then meaningless; the engine reports the failure at the next synchronisation).
+    uint64_t timeout_ns;
+    uint32_t* timed_out;
     // ---- programmatic dependent launch: this launch may start while its predecessor (the previous
     // minibatch) is still draining; everything the predecessor can have written is read only after
     // griddepcontrol.wait.  pdl = 2: the item's own row (from the current table, last written one
@@ -187,6 +192,22 @@ __device__ __forceinline__ void mc_st_f32(float* p, float a) {
 }
 __device__ __forceinline__ void mc_st_release_sys(uint64_t* p, uint64_t v) {
     asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *f >= want, or until the exchange time-out expires (checked every 256 polls).
+__device__ __forceinline__ void wait_flag(const uint64_t* f, uint64_t want, uint64_t timeout_ns, uint32_t* timed_out) {
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0; ld_acquire_sys(f) < want; spins++) {
+        if ((spins & 255u) == 255u && timeout_ns) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) { if (timed_out) atomicExch(timed_out, 1u); return; }
+        }
+    }
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -662,7 +683,7 @@ __device__ __forceinline__ void peer_wait(const BatchParams& p) {
     // with multicast this rank's own rows also come back through the switch: wait for its flag too
     if (threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
         const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
-        while (ld_acquire_sys(f) < p.wait_step) {}
+        wait_flag(f, p.wait_step, p.timeout_ns, p.timed_out);
     }
     __syncthreads();
 }
@@ -776,7 +797,7 @@ __device__ __forceinline__ void grid_barrier(const BatchParams& p, uint32_t* cou
     }
     if (p.n_peers && threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
         const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
-        while (ld_acquire_sys(f) < step) {}
+        wait_flag(f, step, p.timeout_ns, p.timed_out);
     }
     __syncthreads();
 }
@@ -816,7 +837,7 @@ force_epoch_kernel(const EpochParams ep) {
         // rows the peers stored during the previous epoch's last minibatch
         if (threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
             const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
-            while (ld_acquire_sys(f) < ep.step0) {}
+            wait_flag(f, ep.step0, p.timeout_ns, p.timed_out);
         }
         __syncthreads();
     }

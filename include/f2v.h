@@ -144,6 +144,8 @@ int f2v_set_epoch_mode(f2v_engine* e, int mode);
  *   "multicast" peer exchange through NVLink multicast stores: 1 (default) when supported, 0 never
  *   "sharded"   1 = row-sharded tables (set on every rank before f2v_comm_peer_export)
  *   "trace"     1 = record per-minibatch times (f2v_trace_ms)
+ *   "exchange_timeout_ms"  multi-GPU: how long a launch waits for a peer's exchange step before it
+ *               gives up (default 30000; 0 = for ever); f2v_sync / f2v_get_embeddings then fail
  *   "order", "peer_sig", "peer_debug", "epoch_ctas"  development probes (tools/mgpu_probe.py)  */
 int f2v_set_option(f2v_engine* e, const char* name, int64_t value);
 /* Kernel launches issued by this engine since creation (force + sampler kernels).     */

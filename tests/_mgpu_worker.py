@@ -87,6 +87,30 @@ def main():
             if not same:
                 print("rank", rank, comm, "model", model, "bs", bs, "max diff", np.abs(a - b).max(), flush=True)
             ok &= same
+    # a rank that never shows up must be reported, not waited for: rank 0 runs one single-minibatch
+    # epoch alone with a 1.5 s exchange time-out and has to get an error at the synchronisation
+    rp2, ci2 = host.rmat_csr(9, 8, 3)
+    n2 = len(rp2) - 1
+    lonely = F.Engine(rp2, ci2, 32, device=local)
+    lonely.set_option("exchange_timeout_ms", 1500)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, lonely.comm_peer_export())
+    lonely.comm_peer_init(blobs, rank, world)
+    if rank == 0:
+        g2 = host.RandStream(1)
+        lonely.set_embeddings(g2.init_embeddings(5, n2, 32))
+        lonely.set_negatives(g2.epoch_negatives(5, n2, n2, 5, 0).copy())
+        lonely.run_epoch(5, n2, 5, 0, 0.02)
+        try:
+            lonely.sync()
+            print("rank 0: the missing peer was not reported", flush=True)
+            ok = False
+        except F.F2VError as ex:
+            if "timed out" not in str(ex):
+                print("rank 0: unexpected error", ex, flush=True)
+                ok = False
+    dist.barrier()
+    lonely.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
