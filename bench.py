@@ -8,8 +8,12 @@ d=128, one B200.  A "step" is one epoch = one pass of the hot path over every mi
                                                             (oracle/_ref), same config
 
 value    = pair updates / s, inputs resident in HBM, CUDA events around K epochs, max over ranks
+           (N > 1: replicated tables, every minibatch's rows dealt to the ranks, the exchange fused
+           into the force kernel -- NVLink multicast or peer stores; --comm nccl = all-gather baseline,
+           --sharded 1 = row-sharded tables)
 e2e      = the same through f2v_run_epoch_host: pinned HOST table + sample stream in, HOST table
-           out, every step (PCIe copies inside the timed region)
+           out, every step (PCIe copies inside the timed region; N > 1: each rank moves its 1/N
+           share of the table over its own PCIe link, the rest travels over NVLink)
 roofline = algorithmic bytes per force-kernel launch / its average duration over the timed region
            (bytes per epoch = (nnz + n*s)*d*4 read + n*d*4 written)
 cpu_baseline = the unmodified reference (oracle/_ref) on this box's host cores, one epoch sample

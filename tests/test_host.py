@@ -280,3 +280,23 @@ def test_multi_gpu_driver_without_gpus_fails_loudly():
     alg.gpus = 2
     with pytest.raises(capi.F2VError):
         alg.AlgoForce2VecNS(1, 0, 16, 5, 0.02, write=False)
+
+
+@pytest.mark.parametrize("assign", [2, 4, 3, 5])
+def test_plan_item_orders_cover_every_row_once(assign):
+    """Item-order flags (2 = light rows right after the hub chunks, 4 = light rows interleaved; | 1 =
+    balanced ownership): a permutation of the default plan's items, minibatch by minibatch."""
+    rp, ci = host.rmat_csr(11, 16, 1)
+    world = 2 if assign & 1 else 1
+    for rank in range(world):
+        base = host.plan_build(rp, 512, 32, rank=rank, world=world, assign=assign & 1)
+        alt = host.plan_build(rp, 512, 32, rank=rank, world=world, assign=assign)
+        assert np.array_equal(base["item_ptr"], alt["item_ptr"]) and np.array_equal(base["n_hub"], alt["n_hub"])
+        for b in range(base["nb"]):
+            lo, hi = int(base["item_ptr"][b]), int(base["item_ptr"][b + 1])
+            nh = int(base["n_hub"][b])
+            assert np.array_equal(base["items"][lo:lo + nh], alt["items"][lo:lo + nh])      # hub chunks unchanged
+            a = np.sort(base["items"][lo + nh:hi], order=["v", "e0"])
+            c = np.sort(alt["items"][lo + nh:hi], order=["v", "e0"])
+            assert np.array_equal(a, c)
+            assert np.array_equal(alt["hub"]["deg"][lo + nh:hi], alt["items"]["len"][lo + nh:hi])
