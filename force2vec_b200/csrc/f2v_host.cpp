@@ -61,14 +61,94 @@ extern "C" f2v_rng* f2v_rng_create(uint32_t seed) {
 extern "C" void f2v_rng_destroy(f2v_rng* g) { free(g); }
 extern "C" int32_t f2v_rng_next(f2v_rng* g) { return (int32_t)g->next(); }
 
+// ---- jump-ahead.  The raw sequence obeys s[i] = s[i-31] + s[i-3] (mod 2^32), a linear recurrence
+// with characteristic polynomial x^31 - x^28 - 1 over Z/2^32: s[m] = sum_k P_m[k] * w[k] with
+// P_m = x^m mod that polynomial and w the current window of 31 values.  So the state after N draws
+// costs O(31^2 log N) instead of N steps, and a long run of draws (the n*dim initial embedding: 2.1 G
+// at R-MAT 24, d=128) can be cut into chunks that independent threads generate -- the same numbers,
+// in the same places, as the reference's serial loop.
+namespace {
+struct RngPoly { uint32_t c[31]; };
+inline void poly_reduce(uint32_t (&t)[61], RngPoly& out) {
+    for (int k = 60; k >= 31; k--) { t[k - 3] += t[k]; t[k - 31] += t[k]; }       // x^k = x^(k-3) + x^(k-31)
+    for (int k = 0; k < 31; k++) out.c[k] = t[k];
+}
+inline RngPoly poly_mul(const RngPoly& a, const RngPoly& b) {
+    uint32_t t[61] = {0};
+    for (int i = 0; i < 31; i++)
+        for (int j = 0; j < 31; j++) t[i + j] += a.c[i] * b.c[j];
+    RngPoly r;
+    poly_reduce(t, r);
+    return r;
+}
+inline RngPoly poly_mul_x(const RngPoly& a) {                                     // a * x
+    RngPoly r;
+    for (int k = 30; k >= 1; k--) r.c[k] = a.c[k - 1];
+    r.c[0] = a.c[30];                    // x^31 = x^28 + 1
+    r.c[28] += a.c[30];
+    return r;
+}
+inline RngPoly poly_pow_x(uint64_t m) {                                           // x^m mod the polynomial
+    RngPoly result{}, base{};
+    result.c[0] = 1;
+    base.c[1] = 1;
+    while (m) {
+        if (m & 1) result = poly_mul(result, base);
+        base = poly_mul(base, base);
+        m >>= 1;
+    }
+    return result;
+}
+// window of the generator, oldest value first: w[k] = s[i-31+k]
+inline void rng_window(const f2v_rng& g, uint32_t (&w)[31]) {
+    for (int k = 0; k < 31; k++) w[k] = g.r[(g.f + k) % 31];
+}
+// the generator as it will be after `steps` more draws, given P = x^steps
+inline f2v_rng rng_jump(const uint32_t (&w)[31], RngPoly P) {
+    f2v_rng out;
+    for (int j = 0; j < 31; j++) {
+        uint32_t v = 0;
+        for (int k = 0; k < 31; k++) v += P.c[k] * w[k];
+        out.r[j] = v;
+        P = poly_mul_x(P);
+    }
+    out.f = 0;
+    out.b = 28;
+    return out;
+}
+template <bool TDIST>
+inline void init_span(f2v_rng& g, float* X, uint64_t count) {
+    const double denom = 2147483647.0 + 1.0;   // RAND_MAX + 1.0
+    if (TDIST) for (uint64_t k = 0; k < count; k++) X[k] = (float)(-1.0 + 2.0 * (double)g.next() / denom);
+    else for (uint64_t k = 0; k < count; k++) X[k] = (float)((double)g.next() / denom);
+}
+}  // namespace
+
 extern "C" int f2v_init_embeddings(f2v_rng* g, int model, uint64_t n, uint32_t dim, float* X) {
     if (!g || !X) return F2V_ERR_ARG;
-    const double denom = 2147483647.0 + 1.0;   // RAND_MAX + 1.0
     const uint64_t total = n * (uint64_t)dim;
-    if (model == F2V_TDIST)
-        for (uint64_t k = 0; k < total; k++) X[k] = (float)(-1.0 + 2.0 * (double)g->next() / denom);
-    else
-        for (uint64_t k = 0; k < total; k++) X[k] = (float)((double)g->next() / denom);
+    constexpr uint64_t kChunk = 1ull << 20;
+    const uint64_t nchunks = (total + kChunk - 1) / kChunk;
+    if (nchunks <= 1) {
+        if (model == F2V_TDIST) init_span<true>(*g, X, total); else init_span<false>(*g, X, total);
+        return F2V_OK;
+    }
+    // generator states at the chunk starts: P_(c*kChunk) by repeated multiplication with P_kChunk
+    uint32_t w[31];
+    rng_window(*g, w);
+    std::vector<f2v_rng> start(nchunks + 1);
+    start[0] = *g;
+    const RngPoly step = poly_pow_x(kChunk);
+    RngPoly P = step;
+    for (uint64_t c = 1; c < nchunks; c++) { start[c] = rng_jump(w, P); P = poly_mul(P, step); }
+    start[nchunks] = rng_jump(w, poly_pow_x(total));     // the stream continues here (negatives, walks)
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c = 0; c < (int64_t)nchunks; c++) {
+        f2v_rng local = start[c];
+        const uint64_t lo = (uint64_t)c * kChunk, cnt = std::min(kChunk, total - lo);
+        if (model == F2V_TDIST) init_span<true>(local, X + lo, cnt); else init_span<false>(local, X + lo, cnt);
+    }
+    *g = start[nchunks];
     return F2V_OK;
 }
 

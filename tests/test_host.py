@@ -300,3 +300,16 @@ def test_plan_item_orders_cover_every_row_once(assign):
             c = np.sort(alt["items"][lo + nh:hi], order=["v", "e0"])
             assert np.array_equal(a, c)
             assert np.array_equal(alt["hub"]["deg"][lo + nh:hi], alt["items"]["len"][lo + nh:hi])
+
+
+@pytest.mark.parametrize("model", [5, 6])
+def test_parallel_init_equals_serial_stream(oracle, model):
+    """Initial embeddings longer than one chunk (2^20 draws) are generated by independent threads
+    from jump-ahead states of the glibc-compatible generator: the same numbers in the same places as
+    the serial reference loop, and the stream continues where the serial loop would have left it."""
+    n, d = 33000, 100                       # 3.3 M draws: four chunks, the last one partial
+    g, o = host.RandStream(1), oracle.Rng(1)
+    for _ in range(7):                      # start from a state that is not the seed state
+        assert g.rand() == o.rand()
+    assert np.array_equal(g.init_embeddings(model, n, d), oracle.init_embeddings(o, model, n, d))
+    assert [g.rand() for _ in range(64)] == [o.rand() for _ in range(64)]
