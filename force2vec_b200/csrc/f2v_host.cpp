@@ -177,6 +177,33 @@ extern "C" int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint3
     const bool window = bs_mode && model != F2V_WALK;
     const uint64_t W = window ? (uint64_t)batch + s - 1 : (uint64_t)s;
     const uint64_t draws = window ? (uint64_t)s * batch : (uint64_t)s;
+    // bs=1: the reference consumes s*batch draws per minibatch but only ever reads the first
+    // batch+s-1 of them; the unread ones are skipped with one jump-ahead per minibatch
+    // (the skip length is the same every time, so its polynomial is computed once)
+    const uint64_t skip = draws > W ? draws - W : 0;
+    const bool jump = skip >= 4096;
+    if (jump && nb > 1) {
+        // every minibatch consumes exactly `draws` values: the generator states at the minibatch
+        // starts follow from one polynomial, and the minibatches are drawn by independent threads
+        const uint32_t maxv = (uint32_t)(n - 1);
+        uint32_t w[31];
+        rng_window(*g, w);
+        std::vector<f2v_rng> start(nb + 1);
+        start[0] = *g;
+        const RngPoly step = poly_pow_x(draws);
+        RngPoly P = step;
+        for (uint64_t b = 1; b <= nb; b++) { start[b] = rng_jump(w, P); if (b < nb) P = poly_mul(P, step); }
+#pragma omp parallel for schedule(static)
+        for (int64_t b = 0; b < (int64_t)nb; b++) {
+            f2v_rng local = start[b];
+            uint32_t* o = out + (uint64_t)b * W;
+            for (uint64_t k = 0; k < W; k++) o[k] = local.next() % maxv;
+        }
+        *g = start[nb];
+        return F2V_OK;
+    }
+    RngPoly Pskip{};
+    if (jump) Pskip = poly_pow_x(skip);
     for (uint64_t b = 0; b < nb; b++) {
         uint32_t maxv = (uint32_t)(n - 1);
         if (model == F2V_WALK) {
@@ -184,9 +211,14 @@ extern "C" int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint3
             if (pre < maxv) maxv = (uint32_t)pre;
         }
         uint32_t* o = out + b * W;
-        for (uint64_t k = 0; k < draws; k++) {
-            uint32_t r = g->next() % maxv;
-            if (k < W) o[k] = r;      // s*batch draws are consumed, batch+s-1 are ever read
+        const uint64_t kept = std::min(draws, W);
+        for (uint64_t k = 0; k < kept; k++) o[k] = g->next() % maxv;
+        if (jump) {
+            uint32_t w[31];
+            rng_window(*g, w);
+            *g = rng_jump(w, Pskip);
+        } else {
+            for (uint64_t k = kept; k < draws; k++) g->next();
         }
     }
     return F2V_OK;

@@ -313,3 +313,19 @@ def test_parallel_init_equals_serial_stream(oracle, model):
         assert g.rand() == o.rand()
     assert np.array_equal(g.init_embeddings(model, n, d), oracle.init_embeddings(o, model, n, d))
     assert [g.rand() for _ in range(64)] == [o.rand() for _ in range(64)]
+
+
+@pytest.mark.parametrize("model,B", [(5, 1024), (6, 2048), (5, 5000)])
+def test_bs1_negatives_with_jump_ahead_match_serial_draws(oracle, cora, model, B):
+    """bs=1: the reference consumes s*batch draws per minibatch and reads the first batch+s-1.  For
+    large batches the unread draws are skipped by jump-ahead and the minibatches are drawn in
+    parallel: same kept values as the oracle's serial loop, same stream position afterwards."""
+    rp, ci = cora
+    n, s = len(rp) - 1, 5
+    nb, W = (n + B - 1) // B, B + s - 1
+    g, o = host.RandStream(1), oracle.Rng(1)
+    for _ in range(2):
+        neg = g.epoch_negatives(model, n, B, s, 1).reshape(nb, W)
+        for b in range(nb):
+            assert np.array_equal(neg[b], oracle.draw_negatives(o, model, 1, n, B, s, b)[:W])
+    assert [g.rand() for _ in range(8)] == [o.rand() for _ in range(8)]
