@@ -345,6 +345,59 @@ extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out
 
 extern "C" void f2v_free(void* p) { free(p); }
 
+// "%.6g" of a float without printf: what `ostream << float` emits (algorithms.h:126-134).  The six
+// significant digits come from one double multiplication by a power of ten; when the scaled value
+// is within 1e-6 of a rounding tie (where the product's error could flip the last digit) or the
+// value is not finite, snprintf decides.  Returns the number of characters written (no terminator).
+static int format_g6(char* out, float v) {
+    static const double kPow10[] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11, 1e12, 1e13,
+                                    1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    if (v == 0.0f) {
+        int k = 0;
+        if (std::signbit(v)) out[k++] = '-';
+        out[k++] = '0';
+        return k;
+    }
+    const double a = std::fabs((double)v);
+    if (!(a >= 1e-17 && a < 1e17)) return snprintf(out, 32, "%.6g", (double)v);    // rare magnitudes, inf, nan
+    int e10 = (int)std::floor(std::log10(a));
+    double scaled = e10 <= 5 ? a * kPow10[5 - e10] : a / kPow10[e10 - 5];
+    if (scaled < 1e5) { e10--; scaled = e10 <= 5 ? a * kPow10[5 - e10] : a / kPow10[e10 - 5]; }
+    else if (scaled >= 1e6) { e10++; scaled = e10 <= 5 ? a * kPow10[5 - e10] : a / kPow10[e10 - 5]; }
+    const double fl = std::floor(scaled), frac = scaled - fl;
+    if (std::fabs(frac - 0.5) < 1e-6 || scaled < 1e5 || scaled >= 1e6) return snprintf(out, 32, "%.6g", (double)v);
+    uint32_t digits = (uint32_t)fl + (frac > 0.5 ? 1u : 0u);
+    if (digits >= 1000000u) { digits = 100000u; e10++; }
+    char d[6];
+    for (int k = 5; k >= 0; k--) { d[k] = (char)('0' + digits % 10); digits /= 10; }
+    int nd = 6;
+    while (nd > 1 && d[nd - 1] == '0') nd--;                   // %g drops trailing zeros
+    int k = 0;
+    if (v < 0) out[k++] = '-';
+    if (e10 < -4 || e10 >= 6) {                                 // d.ddddde[+-]XX
+        out[k++] = d[0];
+        if (nd > 1) { out[k++] = '.'; for (int i = 1; i < nd; i++) out[k++] = d[i]; }
+        out[k++] = 'e';
+        int e = e10;
+        if (e < 0) { out[k++] = '-'; e = -e; } else out[k++] = '+';
+        if (e >= 100) { out[k++] = (char)('0' + e / 100); e %= 100; }
+        out[k++] = (char)('0' + e / 10);
+        out[k++] = (char)('0' + e % 10);
+    } else if (e10 >= 0) {                                      // ddd.ddd
+        const int ip = e10 + 1;                                 // digits before the point
+        for (int i = 0; i < ip; i++) out[k++] = i < nd ? d[i] : '0';
+        if (nd > ip) { out[k++] = '.'; for (int i = ip; i < nd; i++) out[k++] = d[i]; }
+    } else {                                                    // 0.000ddd
+        out[k++] = '0'; out[k++] = '.';
+        for (int i = 0; i < -e10 - 1; i++) out[k++] = '0';
+        for (int i = 0; i < nd; i++) out[k++] = d[i];
+    }
+    return k;
+}
+
+// exposed for the test that compares it with printf on millions of values
+extern "C" int f2v_format_g6(float v, char* out32) { int k = format_g6(out32, v); out32[k] = 0; return k; }
+
 extern "C" int f2v_write_embd(const char* path, const float* X, uint64_t n, uint32_t dim) {
     if (!path || !X) return F2V_ERR_ARG;
     FILE* f = fopen(path, "wb");
@@ -369,7 +422,8 @@ extern "C" int f2v_write_embd(const char* path, const float* X, uint64_t n, uint
                 s.append(tmp, k);
                 const float* row = X + i * dim;
                 for (uint32_t d = 0; d < dim; d++) {
-                    k = snprintf(tmp, sizeof(tmp), "%.6g ", (double)row[d]);
+                    k = format_g6(tmp, row[d]);
+                    tmp[k++] = ' ';
                     s.append(tmp, k);
                 }
                 s.push_back('\n');

@@ -48,6 +48,9 @@ void f2v_free(void* p);
 /* "N D" header, then "id v1 .. vD " per row with 6 significant digits and a trailing
  * space (algorithms.h:118-136).                                                           */
 int  f2v_write_embd(const char* path, const float* X, uint64_t n, uint32_t dim);
+/* "%.6g" of one value as the writer formats it (fast path + printf fall-back); out32: >= 32 bytes.
+ * Exposed for tests.                                                                       */
+int  f2v_format_g6(float v, char* out32);
 /* Writes the lower triangle as "%%MatrixMarket matrix coordinate pattern symmetric".      */
 int  f2v_write_mtx(const char* path, uint64_t n, const uint64_t* rowptr, const uint32_t* colids);
 

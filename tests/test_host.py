@@ -329,3 +329,24 @@ def test_bs1_negatives_with_jump_ahead_match_serial_draws(oracle, cora, model, B
         for b in range(nb):
             assert np.array_equal(neg[b], oracle.draw_negatives(o, model, 1, n, B, s, b)[:W])
     assert [g.rand() for _ in range(8)] == [o.rand() for _ in range(8)]
+
+
+def test_fast_g6_formatter_equals_printf():
+    """The .embd writer formats values itself ("%.6g" = ostream's default, algorithms.h:126-134);
+    compare with the C library's formatting on random values of every magnitude, ties, zeros, inf."""
+    import ctypes as C
+    L = F.lib()
+    buf = C.create_string_buffer(40)
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([
+        rng.random(60000, dtype=np.float32) * 2 - 1,
+        rng.standard_normal(30000).astype(np.float32) * 1e-5,
+        (rng.random(30000) * 1e7).astype(np.float32),
+        rng.integers(0, 2 ** 32, 60000, dtype=np.uint64).astype(np.uint32).view(np.float32),     # any bit pattern
+        np.array([0.0, -0.0, 1, -1, 0.5, 1e-5, 9.99999e-5, 1e-4, 123456, 1234567, 999999.5, 999999.4, 0.1, 1e6, 1e5,
+                  99999.95, 1e-10, 3.4e38, 1e-40, np.inf, -np.inf, 0.02, -0.1, 5, -5, 100000, 999999, 1000000,
+                  2.5e-5, 0.000123456789, 0.15625, 2.5, 1.5e-7], np.float32)])
+    vals = vals[~np.isnan(vals)]            # printf prints the sign of a NaN, Python does not
+    for v in vals:
+        L.f2v_format_g6(C.c_float(float(v)), buf)
+        assert buf.value.decode() == "%.6g" % float(v), repr(float(v))
