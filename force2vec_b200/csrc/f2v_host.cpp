@@ -409,28 +409,30 @@ extern "C" int f2v_write_embd(const char* path, const float* X, uint64_t n, uint
 #ifdef _OPENMP
     nt = omp_get_max_threads();
 #endif
-    std::vector<std::string> out(nt);
+    // worst case per value: "-1.23457e-38 " = 13 characters; per row: a 20-digit id, a space, a newline
+    const size_t row_cap = 24 + (size_t)dim * 16;
+    std::vector<std::vector<char>> out(nt);
+    std::vector<size_t> used(nt, 0);
+    for (int t = 0; t < nt; t++) out[t].resize(row_cap * block);
     for (uint64_t base = 0; base < n; base += block * nt) {
 #pragma omp parallel for schedule(static, 1) num_threads(nt)
         for (int t = 0; t < nt; t++) {
-            std::string& s = out[t];
-            s.clear();
+            char* s = out[t].data();
+            size_t k = 0;
             uint64_t lo = base + (uint64_t)t * block, hi = std::min(n, lo + block);
-            char tmp[64];
             for (uint64_t i = lo; i < hi; i++) {
-                int k = snprintf(tmp, sizeof(tmp), "%llu ", (unsigned long long)(i + 1));
-                s.append(tmp, k);
+                k += (size_t)snprintf(s + k, 24, "%llu ", (unsigned long long)(i + 1));
                 const float* row = X + i * dim;
                 for (uint32_t d = 0; d < dim; d++) {
-                    k = format_g6(tmp, row[d]);
-                    tmp[k++] = ' ';
-                    s.append(tmp, k);
+                    k += (size_t)format_g6(s + k, row[d]);
+                    s[k++] = ' ';
                 }
-                s.push_back('\n');
+                s[k++] = '\n';
             }
+            used[t] = lo < hi ? k : 0;
         }
         for (int t = 0; t < nt; t++)
-            if (!out[t].empty()) fwrite(out[t].data(), 1, out[t].size(), f);
+            if (used[t]) fwrite(out[t].data(), 1, used[t], f);
     }
     int rc = ferror(f) ? F2V_ERR_ARG : F2V_OK;
     fclose(f);
