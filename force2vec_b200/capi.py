@@ -20,7 +20,7 @@ ENGINE_SYMBOLS = [
 HOST_SYMBOLS = [
     "f2v_rng_create", "f2v_rng_destroy", "f2v_rng_next", "f2v_init_embeddings", "f2v_build_lut",
     "f2v_neg_stream_len", "f2v_draw_epoch_negatives", "f2v_draw_walks", "f2v_load_mtx", "f2v_free",
-    "f2v_write_embd", "f2v_format_g6", "f2v_write_mtx", "f2v_rmat_csr", "f2v_plan_build", "f2v_train", "f2v_train_gpus",
+    "f2v_write_embd", "f2v_format_g6", "f2v_write_csr", "f2v_load_csr", "f2v_write_mtx", "f2v_rmat_csr", "f2v_plan_build", "f2v_train", "f2v_train_gpus",
 ]
 
 
@@ -101,6 +101,8 @@ def lib():
     L.f2v_free.argtypes = [vp]
     L.f2v_write_embd.argtypes = [C.c_char_p, vp, u64, u32]
     L.f2v_format_g6.argtypes = [f32, C.c_char_p]
+    L.f2v_write_csr.argtypes = [C.c_char_p, u64, u64, vp, vp]
+    L.f2v_load_csr.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
     L.f2v_write_mtx.argtypes = [C.c_char_p, u64, vp, vp]
     L.f2v_rmat_csr.argtypes = [i32, i32, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
     L.f2v_plan_build.argtypes = [vp, u64, u64, u32, u32, u32, i32, i32, i32, i32, C.POINTER(u64), C.POINTER(vp),

@@ -70,6 +70,18 @@ def load_mtx(path):
     return _take_csr(n, nnz, rp, ci)
 
 
+def write_csr(path, rowptr, colids):
+    ci = colids if len(colids) else np.zeros(1, np.uint32)
+    check(lib().f2v_write_csr(path.encode(), len(rowptr) - 1, len(colids), _p(rowptr), _p(ci)), "f2v_write_csr")
+
+
+def load_csr(path):
+    n, nnz, rp, ci = C.c_uint64(), C.c_uint64(), C.c_void_p(), C.c_void_p()
+    check(lib().f2v_load_csr(path.encode(), C.byref(n), C.byref(nnz), C.byref(rp), C.byref(ci)),
+          "f2v_load_csr(%s)" % path)
+    return _take_csr(n, nnz, rp, ci)
+
+
 def rmat_csr(scale, edge_factor=16, seed=1):
     n, nnz, rp, ci = C.c_uint64(), C.c_uint64(), C.c_void_p(), C.c_void_p()
     check(lib().f2v_rmat_csr(scale, edge_factor, seed, C.byref(n), C.byref(nnz), C.byref(rp), C.byref(ci)),

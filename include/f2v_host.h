@@ -48,6 +48,11 @@ void f2v_free(void* p);
 /* "N D" header, then "id v1 .. vD " per row with 6 significant digits and a trailing
  * space (algorithms.h:118-136).                                                           */
 int  f2v_write_embd(const char* path, const float* X, uint64_t n, uint32_t dim);
+/* Binary CSR cache (magic "F2VCSR01", n, nnz, rowptr u64, colids u32): the fast path for graphs
+ * whose text form takes minutes to parse.  f2v_load_csr validates the arrays; release with f2v_free.
+ * The CLI reads it when -input ends in ".f2vcsr".                                           */
+int  f2v_write_csr(const char* path, uint64_t n, uint64_t nnz, const uint64_t* rowptr, const uint32_t* colids);
+int  f2v_load_csr(const char* path, uint64_t* n, uint64_t* nnz, uint64_t** rowptr, uint32_t** colids);
 /* "%.6g" of one value as the writer formats it (fast path + printf fall-back); out32: >= 32 bytes.
  * Exposed for tests.                                                                       */
 int  f2v_format_g6(float v, char* out32);

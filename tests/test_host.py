@@ -350,3 +350,23 @@ def test_fast_g6_formatter_equals_printf():
     for v in vals:
         L.f2v_format_g6(C.c_float(float(v)), buf)
         assert buf.value.decode() == "%.6g" % float(v), repr(float(v))
+
+
+def test_binary_csr_cache_round_trip(tmp_path):
+    rp, ci = host.rmat_csr(10, 8, 4)
+    p = str(tmp_path / "g.f2vcsr")
+    host.write_csr(p, rp, ci)
+    rp2, ci2 = host.load_csr(p)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    raw = bytearray(open(p, "rb").read())
+    raw[0] = ord("X")                                   # wrong magic
+    open(p, "wb").write(raw)
+    with pytest.raises(F.F2VError):
+        host.load_csr(p)
+    raw[0] = ord("F")
+    raw[-4:] = (1 << 31).to_bytes(4, "little")          # a column id out of range
+    open(p, "wb").write(raw)
+    with pytest.raises(F.F2VError):
+        host.load_csr(p)
+    with pytest.raises(F.F2VError):
+        host.load_csr(str(tmp_path / "missing.f2vcsr"))
