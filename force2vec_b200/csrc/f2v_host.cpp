@@ -321,23 +321,78 @@ extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out
     skip_line();
     const uint64_t n = std::max(m, ncol);
     if (n < 1 || n > 0xffffffffull) return F2V_ERR_ARG;
+    // The entry lines are parsed by all host threads: the data region is cut at line boundaries, every
+    // piece yields its (row, col) pairs in file order, and the first `cnt` entries of the file are
+    // kept (the size line decides how many there are, IO.h:95-106); which thread parsed an entry does
+    // not matter, the CSR builder sorts every row.
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    const uint64_t region = (uint64_t)(end - p);
+    if (region < (1u << 20)) nt = 1;
+    std::vector<const char*> cut(nt + 1);
+    cut[0] = p;
+    cut[nt] = end;
+    for (int t = 1; t < nt; t++) {
+        const char* q = p + region * (uint64_t)t / (uint64_t)nt;
+        const char* eol = (const char*)memchr(q, '\n', end - q);
+        cut[t] = eol ? eol + 1 : end;
+    }
+    for (int t = 1; t <= nt; t++) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    std::vector<std::vector<uint32_t>> rows(nt), cols(nt);
+    std::vector<int> bad(nt, 0);
+    // malformed or out-of-range entries are recorded as (0xffffffff, position) and judged afterwards:
+    // only entries among the first `cnt` of the file are errors
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+    for (int t = 0; t < nt; t++) {
+        const char* q = cut[t];
+        const char* qe = cut[t + 1];
+        auto num = [&](uint64_t& v) -> bool {
+            while (q < qe && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+            if (q >= qe || *q < '0' || *q > '9') return false;
+            v = 0;
+            while (q < qe && *q >= '0' && *q <= '9') v = v * 10 + (uint64_t)(*q++ - '0');
+            return true;
+        };
+        std::vector<uint32_t>& R = rows[t];
+        std::vector<uint32_t>& Cc = cols[t];
+        R.reserve((size_t)((qe - q) / 8));
+        Cc.reserve((size_t)((qe - q) / 8));
+        while (q < qe) {
+            while (q < qe && (*q == '\n' || *q == '\r')) q++;
+            if (q >= qe) break;
+            uint64_t r = 0, c = 0;
+            const bool ok = num(r) && num(c) && r >= 1 && c >= 1 && r <= n && c <= n;
+            const char* eol = (const char*)memchr(q, '\n', qe - q);   // the value column is never used
+            q = eol ? eol + 1 : qe;
+            R.push_back(ok ? (uint32_t)(r - 1) : 0xffffffffu);
+            Cc.push_back(ok ? (uint32_t)(c - 1) : 0u);
+        }
+    }
+    uint64_t have = 0;
+    for (int t = 0; t < nt; t++) have += rows[t].size();
+    if (have < cnt) return F2V_ERR_ARG;                       // fewer entries than the size line says
     std::vector<uint32_t> src, dst;
     src.reserve(symmetric ? 2 * cnt : cnt);
     dst.reserve(symmetric ? 2 * cnt : cnt);
-    for (uint64_t k = 0; k < cnt; k++) {
-        while (p < end && (*p == '\n' || *p == '\r')) p++;
-        uint64_t r, c;
-        if (!parse_u(r) || !parse_u(c)) return F2V_ERR_ARG;   // fewer entries than the size line says
-        skip_line();                                           // the value column is never used
-        if (r < 1 || c < 1 || r > n || c > n) return F2V_ERR_ARG;
-        r--; c--;
-        if (symmetric) {
-            if (r == c) continue;                              // self-loops dropped (IO.h:130-134)
-            src.push_back((uint32_t)r); dst.push_back((uint32_t)c);
-            src.push_back((uint32_t)c); dst.push_back((uint32_t)r);   // mirrored (IO.h:122-129)
-        } else {
-            src.push_back((uint32_t)r); dst.push_back((uint32_t)c);
+    uint64_t taken = 0;
+    for (int t = 0; t < nt && taken < cnt; t++) {
+        const uint64_t m_t = std::min<uint64_t>(rows[t].size(), cnt - taken);
+        for (uint64_t k = 0; k < m_t; k++) {
+            const uint32_t r = rows[t][k], c = cols[t][k];
+            if (r == 0xffffffffu) return F2V_ERR_ARG;          // malformed entry / index out of range
+            if (symmetric) {
+                if (r == c) continue;                          // self-loops dropped (IO.h:130-134)
+                src.push_back(r); dst.push_back(c);
+                src.push_back(c); dst.push_back(r);            // mirrored (IO.h:122-129)
+            } else {
+                src.push_back(r); dst.push_back(c);
+            }
         }
+        taken += m_t;
+        std::vector<uint32_t>().swap(rows[t]);
+        std::vector<uint32_t>().swap(cols[t]);
     }
     *n_out = n;
     return csr_from_pairs(n, src, dst, /*dedupe=*/false, nnz_out, rowptr_out, colids_out);
