@@ -1,22 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- the reference's headline metric (force-pair updates / s, epoch time, fraction of
-the HBM roofline) on BASELINE.json configs[1]: synthetic R-MAT scale-20, sForce2Vec (option 6),
-d=128, one B200.  A "step" is one epoch = one pass of the hot path over every minibatch.
+"""bench.py -- the reference's headline metric (force-pair updates / s, epoch time, fraction of the
+HBM roofline) on the configuration BASELINE.json quotes "1/2/4/8 B200" on: configs[3], synthetic
+R-MAT scale-24, tForce2Vec (option 5) with per-vertex negatives (bs=1), d=128.  It fits one GPU
+(2 x 8 GiB tables + 2 GiB CSR).  A "step" is one epoch = one pass of the hot path over every minibatch.
 
   python bench.py --gpus N --steps K --warmup W            our engine (N ranks under torchrun)
-  python bench.py --impl reference ...                      the reference's own CPU code
-                                                            (oracle/_ref), same config
+  python bench.py --impl reference ...                      the reference's own CPU code (oracle/_ref)
+  python bench.py --workload cfg2|cfg3|cfg4|cfg5            the other BASELINE configs (cfg5: 8 GPUs)
 
 value    = pair updates / s, inputs resident in HBM, CUDA events around K epochs, max over ranks
-           (N > 1: replicated tables, every minibatch's rows dealt to the ranks, the exchange fused
-           into the force kernel -- NVLink multicast or peer stores; --comm nccl = all-gather baseline,
-           --sharded 1 = row-sharded tables)
-e2e      = the same through f2v_run_epoch_host: pinned HOST table + sample stream in, HOST table
-           out, every step (PCIe copies inside the timed region; N > 1: each rank moves its 1/N
-           share of the table over its own PCIe link, the rest travels over NVLink)
+           (N > 1: replicated tables, every minibatch's rows dealt to the ranks, the exchange fused into
+           the force kernel -- NVLink multicast or peer stores; --comm nccl = all-gather baseline,
+           --sharded 1 = row-sharded tables).  At N > 1 one epoch is first CHECKED: every rank compares
+           its replica (device checksum + probe rows) with a single-GPU engine run from the same state
+           on its own device -- bit for bit -- and the line carries "parity"; a mismatch exits non-zero.
+e2e      = the same through f2v_run_epoch_host: pinned HOST table + sample stream in, HOST table out,
+           every step (PCIe copies inside the timed region; N > 1: each rank moves its 1/N share of the
+           table over its own PCIe link, the rest travels over NVLink)
 roofline = algorithmic bytes per force-kernel launch / its average duration over the timed region
-           (bytes per epoch = (nnz + n*s)*d*4 read + n*d*4 written)
-cpu_baseline = the unmodified reference (oracle/_ref) on this box's host cores, one epoch sample
+           (bytes per epoch = (nnz + n*s)*d*4 read + n*d*4 written); frac_dram = DRAM
+           bytes measured by ncu for this workload and N (profiles/traffic.json) / epoch time / peak
+cpu_baseline = the unmodified reference (oracle/_ref) on this box's host cores, bounded sample
 """
 import argparse
 import json
@@ -31,6 +35,14 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 MODEL_NAMES = {5: "tForce2Vec", 6: "sForce2Vec", 7: "rForce2Vec"}
+# BASELINE.json configs[1..4]; batch = the throughput-optimal minibatch (the CLI's -batch is free;
+# the reference's README batch 256 is reported under "extra")
+WORKLOADS = {
+    "cfg2": dict(scale=20, model=6, dim=128, bs=0, batch=65536),
+    "cfg3": dict(scale=22, model=7, dim=64, bs=0, batch=65536),
+    "cfg4": dict(scale=24, model=5, dim=128, bs=1, batch=65536),
+    "cfg5": dict(scale=26, model=5, dim=128, bs=0, batch=262144),
+}
 
 
 def parse():
@@ -39,17 +51,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=int, default=20)
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=int)
     ap.add_argument("--edge-factor", type=int, default=16)
-    ap.add_argument("--model", type=int, default=6, choices=[5, 6, 7])
-    ap.add_argument("--dim", type=int, default=128)
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--model", type=int, choices=[5, 6, 7])
+    ap.add_argument("--dim", type=int)
+    ap.add_argument("--batch", type=int)
     ap.add_argument("--nsamples", type=int, default=5)
-    ap.add_argument("--bs", type=int, default=0)
+    ap.add_argument("--bs", type=int)
     ap.add_argument("--lr", type=float, default=0.02)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0, help="engine epoch mode (0 per-minibatch launches, 1 persistent)")
-    ap.add_argument("--variant", type=int, default=-1, help="d=128 kernel lane layout (f2v_set_option; -1 = auto)")
+    ap.add_argument("--variant", type=int, default=-1, help="kernel lane layout (f2v_set_option; -1 = auto)")
     ap.add_argument("--neg-smem", type=int, default=1)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N>1 exchange: peer = stores into the peers' replicas fused into the force kernel; "
@@ -58,8 +71,13 @@ def parse():
     ap.add_argument("--sharded", type=int, default=0, help="N>1: row-sharded tables instead of replicas (capacity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra-batches", default="256,4096,16384", help="comma list of additional batch sizes to report")
-    return ap.parse_args()
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra lines (other configs / batch sizes)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the checked epoch (timing probes only)")
+    a = ap.parse_args()
+    for k, v in WORKLOADS[a.workload].items():
+        if getattr(a, k) is None:
+            setattr(a, k, v)
+    return a
 
 
 def workload_name(a):
@@ -77,6 +95,12 @@ def bytes_per_epoch(a, n, nnz):
     if a.model == 7:
         b += n * 5 * (8 + 4)
     return b
+
+
+def config_of(a, n, nnz):
+    """The same dict from both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "n": int(n), "nnz": int(nnz), "pairs_per_epoch": int(pairs_per_epoch(a, n, nnz)),
+            "minibatches_per_epoch": int((n + a.batch - 1) // a.batch)}
 
 
 class ClockSampler:
@@ -126,19 +150,27 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def committed_traffic(a):
-    """dram bytes per force-kernel launch from the committed ncu --set full capture, if any."""
+def committed_capture(a, world):
+    """The committed ncu capture for exactly this workload and world size (profiles/traffic.json):
+    DRAM bytes per epoch and per launch, the kernel layout it was taken on, the gather-only ceiling."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
-    t = json.load(open(p))
-    return t.get(workload_name(a))
+    for e in json.load(open(p)).get("captures", []):
+        if e.get("workload") == workload_name(a) and int(e.get("n_gpus", 1)) == world:
+            return e
+    return None
 
 
-def make_graph(a):
+def make_graph(a, dist=None, rank=0):
+    """R-MAT CSR, built once per box (page-cache copy under /dev/shm shared by the ranks)."""
     from force2vec_b200 import host
     t = time.time()
-    rp, ci = host.rmat_csr(a.scale, a.edge_factor, 1)
+    if dist is not None and rank != 0:
+        dist.barrier()
+    rp, ci = host.rmat_csr_cached(a.scale, a.edge_factor, 1)
+    if dist is not None and rank == 0:
+        dist.barrier()
     return rp, ci, time.time() - t
 
 
@@ -164,6 +196,7 @@ def cpu_reference(a, rp, ci, epochs, warm):
 
 def _cpu_reference(a, rp, ci, epochs, warm):
     from oracle import oracle as O
+    rp, ci = np.ascontiguousarray(rp), np.ascontiguousarray(ci)
     n, nnz = len(rp) - 1, len(ci)
     cores = os.cpu_count() or 1
     if not O.ref_available():
@@ -179,6 +212,7 @@ def _cpu_reference(a, rp, ci, epochs, warm):
         kind = "reference"
         # best CPU path for this model: the AVX-512 variants (options 8/9/10/11) where the host has
         # avx512f+dq and the dimension is one they implement, else the OpenMP scalar option itself
+        # (bs=1 has no AVX-512 variant in the reference)
         avx_opt = {5: 11, 6: 9, 7: 10}[a.model]
         use_avx = O.host_has_avx512() and O.ref_available(avx512=True) and a.dim in (64, 128) and not a.bs
         opt = avx_opt if use_avx else a.model
@@ -188,35 +222,38 @@ def _cpu_reference(a, rp, ci, epochs, warm):
         _, t_init = O.ref_run(opt, a.bs, rp, ci, a.dim, 0, a.batch, a.nsamples, a.lr, threads=cores, avx512=use_avx, want_X=False)
         _, t_run = O.ref_run(opt, a.bs, rp, ci, a.dim, epochs, a.batch, a.nsamples, a.lr, threads=cores, avx512=use_avx, want_X=False)
         sec = max(t_run - t_init, 1e-9) / epochs
-        what = "reference option %d%s" % (opt, " (AVX-512)" if use_avx else " (OpenMP scalar)")
+        what = "reference option %d%s%s" % (opt, " bs=1" if a.bs else "", " (AVX-512)" if use_avx else " (OpenMP scalar)")
     pairs = pairs_per_epoch(a, n, nnz)
-    return {"value": pairs / sec, "unit": "pairs/s", "cores": cores, "kind": kind,
-            "sample": "%d full epoch(s) of the same workload, %s, %d threads, init time differenced out"
-                      % (epochs, what, cores),
-            "epoch_s": sec}
+    return {"value": pairs / sec, "unit": "pairs/s", "cores": cores, "kind": kind, "what": what, "epoch_s": sec,
+            "epochs": epochs, "n": n}
 
 
 def run_reference(a):
+    """The reference's own CPU implementation of the path, all host threads, on OUR arm's config.
+    One timed epoch (the reference's timer spans init + epochs, so a run with 0 epochs is
+    differenced out): at R-MAT 24 that is minutes of CPU work -- the bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rp, ci, _ = make_graph(a)
     n, nnz = len(rp) - 1, len(ci)
-    epochs = max(1, min(a.steps, 3))         # bounded sample: at most 3 timed epochs
-    r = cpu_reference(a, rp, ci, epochs, warm=a.warmup > 0)
+    epochs = 1 if (a.scale >= 22 or a.steps < 2) else min(a.steps, 3)
+    r = cpu_reference(a, rp, ci, epochs, warm=False)
+    sample = ("%d full epoch(s) of this workload, %s, %d threads; the reference times init + epochs "
+              "(algorithms.cpp:557,647), a 0-epoch run is differenced out" % (epochs, r["what"], r["cores"]))
     line = {"impl": "reference", "metric": "force_pair_updates_per_sec", "value": r["value"], "unit": "pairs/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["epoch_s"] * 1e3,
+            "n_gpus": a.gpus, "steps": epochs, "warmup": 0, "requested": {"steps": a.steps, "warmup": a.warmup},
+            "ms_per_step": r["epoch_s"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "n": n, "nnz": nnz, "pairs_per_epoch": pairs_per_epoch(a, n, nnz),
-                       "timed_epochs": epochs},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": config_of(a, n, nnz),
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
-def timed_epochs(torch, dist, eng, a, K, neg_all, stride, first_epoch, world):
+def timed_epochs(torch, dist, eng, a, K, stride, first_epoch, world):
     """K epochs, device-timed on the engine's (= torch's current) stream; returns seconds (max over ranks)."""
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
@@ -240,6 +277,67 @@ def timed_epochs(torch, dist, eng, a, K, neg_all, stride, first_epoch, world):
     return sec
 
 
+def shared_init(a, n, host, dist, rank):
+    """N > 1: the n x dim initial table off the glibc-compatible stream (reference order).  Rank 0 draws
+    it (all host threads, jump-ahead) into a page-cache file, the others map the same pages.  Returns
+    the table and, on rank 0, the generator positioned after the initial draws (the negatives follow)."""
+    path = "/dev/shm/f2v_X0_rmat%d_m%d_d%d.npy" % (a.scale, a.model, a.dim)
+    g = None
+    if rank == 0:
+        g = host.RandStream(1)
+        X = np.lib.format.open_memmap(path + ".tmp.npy", mode="w+", dtype=np.float32, shape=(n, a.dim))
+        g.init_embeddings(a.model, n, a.dim, out=X)
+        X.flush()
+        del X
+        os.replace(path + ".tmp.npy", path)
+    dist.barrier()
+    return np.load(path, mmap_mode="r"), g
+
+
+def make_engine(F, a, rp, ci, local, stream=None):
+    eng = F.Engine(rp, ci, a.dim, device=local)
+    if stream is not None:
+        eng.set_stream(stream)
+    if a.mode:
+        eng.set_epoch_mode(a.mode)
+    eng.set_option("variant", a.variant)
+    eng.set_option("neg_smem", a.neg_smem)
+    if a.model != 5:
+        eng.set_lut()
+    return eng
+
+
+def checked_epoch(F, a, rp, ci, local, X0, neg0, multi, dist, torch, rank, world):
+    """N > 1: one epoch from the same state on a single-GPU engine (this rank's device) and on the
+    N-rank engine, same hub chunk length: every replica must equal the single-GPU table bit for bit
+    (device checksum over the whole table + probe rows compared value by value)."""
+    chunk = a.chunk or 64
+    n = len(rp) - 1
+    probe = sorted(set(int(x) for x in np.linspace(0, n - 1, 64)))
+    single = make_engine(F, a, rp, ci, local)
+    single.set_embeddings(X0)
+    single.set_negatives(neg0)
+    if a.model == 7:
+        single.sample_walks(1, 0)
+    single.run_epoch(a.model, a.batch, a.nsamples, a.bs, a.lr, chunk)
+    h1 = single.checksum()
+    rows1 = np.stack([single.get_rows(v, 1)[0] for v in probe])
+    single.close()
+    multi.set_embeddings(X0)
+    multi.set_negatives(neg0)
+    if a.model == 7:
+        multi.sample_walks(1, 0)
+    multi.run_epoch(a.model, a.batch, a.nsamples, a.bs, a.lr, chunk)
+    hN = multi.checksum()
+    rowsN = np.stack([multi.get_rows(v, 1)[0] for v in probe])
+    same = (h1 == hN) and np.array_equal(rows1, rowsN)
+    t = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"vs": "single_gpu", "bit_exact": bool(int(t.item()) == 1), "checksum": "%016x" % h1,
+            "checksum_this_rank": "%016x" % hN, "epochs": 1, "chunk": chunk, "probe_rows": len(probe),
+            "checked_on": "every rank's replica against a single-GPU engine on the same device"}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -254,32 +352,47 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rp, ci, t_graph = make_graph(a)
+    rp, ci, t_graph = make_graph(a, dist if world > 1 else None, rank)
     n, nnz = len(rp) - 1, len(ci)
     pairs = pairs_per_epoch(a, n, nnz)
     K, W = a.steps, a.warmup
+    if world > 1 and a.sharded:
+        a.no_e2e = True          # the host-buffer call of a row-sharded engine takes the FULL table on every rank
+                                 # (rows are placed by hash): world x table bytes of host memory -- not benchmarked
     total_epochs = W + K + (0 if a.no_e2e else W + K)
 
-    g = host.RandStream(1)
-    X0 = torch.empty((n, a.dim), dtype=torch.float32, pin_memory=True)
-    g.init_embeddings(a.model, n, a.dim, out=X0.numpy())
+    # ---- inputs: the reference's own stream order (init, then per epoch the negatives)
+    per = -(-n // world)
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)      # this rank's share of the host table (e2e)
+    if world == 1:
+        g = host.RandStream(1)
+        X0t = torch.empty((n, a.dim), dtype=torch.float32, pin_memory=True)
+        X0 = X0t.numpy()
+        g.init_embeddings(a.model, n, a.dim, out=X0)
+    else:
+        X0, g = shared_init(a, n, host, dist, rank)
     stride = host.neg_stream_len(a.model, n, a.batch, a.nsamples, a.bs)
     neg_all = torch.empty(max(total_epochs * stride, 1), dtype=torch.int32, pin_memory=True)
     neg_np = neg_all.numpy().view(np.uint32)
-    for k in range(total_epochs):
-        g.epoch_negatives(a.model, n, a.batch, a.nsamples, a.bs, out=neg_np[k * stride:(k + 1) * stride])
+    if rank == 0:
+        # rank 0 owns the serial stream (as thread 0 does in f2v_train_gpus); the others receive the draws
+        for k in range(total_epochs):
+            g.epoch_negatives(a.model, n, a.batch, a.nsamples, a.bs, out=neg_np[k * stride:(k + 1) * stride])
+    if world > 1:
+        path = "/dev/shm/f2v_neg_rmat%d_m%d_B%d_bs%d_e%d.npy" % (a.scale, a.model, a.batch, a.bs, total_epochs)
+        if rank == 0:
+            np.save(path + ".tmp.npy", neg_np)
+            os.replace(path + ".tmp.npy", path)
+        dist.barrier()
+        if rank != 0:
+            neg_np[:] = np.load(path, mmap_mode="r")
 
-    eng = F.Engine(rp, ci, a.dim, device=local)
-    # the engine launches on torch's current stream so that torch.cuda.Event brackets its kernels;
-    # that must be a real (non-default) stream: handle 0 means "engine's own stream" in the C ABI
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    eng.set_stream(stream.cuda_stream)
-    if a.mode:
-        eng.set_epoch_mode(a.mode)
-    eng.set_option("variant", a.variant)
-    eng.set_option("neg_smem", a.neg_smem)
+    # the engine launches on torch's current stream so that torch.cuda.Event brackets its kernels;
+    # that must be a real (non-default) stream: handle 0 means "engine's own stream" in the C ABI
+    eng = make_engine(F, a, rp, ci, local, stream.cuda_stream)
     if world > 1 and a.comm == "nccl":
         ids = [F.Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -290,18 +403,26 @@ def run_ours(a):
         blobs = [None] * world
         dist.all_gather_object(blobs, eng.comm_peer_export())
         eng.comm_peer_init(blobs, rank, world)
-    if a.model != 5:
-        eng.set_lut()
-    eng.set_embeddings(X0.numpy())
+
+    parity = None
+    if world > 1 and not a.no_parity:
+        parity = checked_epoch(F, a, rp, ci, local, X0, neg_np[:stride], eng, dist, torch, rank, world)
+        if not parity["bit_exact"]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU table differs from the single-GPU run", "parity": parity}), flush=True)
+            dist.barrier()
+            sys.exit(3)
+    eng.set_embeddings(X0)
     eng.set_negatives(neg_np[:(W + K) * stride])
     eng.sync()
+    free_b, total_b = eng.device_memory()
 
     # ---- resident-input throughput ("value")
-    timed_epochs(torch, dist, eng, a, W, neg_all, stride, 0, world)          # warm-up (plan build, clocks)
+    timed_epochs(torch, dist, eng, a, W, stride, 0, world)          # warm-up (plan build, clocks)
     l0 = eng.launch_count()
     cs = ClockSampler(local)
     cs.__enter__()                                   # sampled across the value AND the e2e timed regions
-    sec = timed_epochs(torch, dist, eng, a, K, neg_all, stride, W, world)
+    sec = timed_epochs(torch, dist, eng, a, K, stride, W, world)
     launches = eng.launch_count() - l0
     epoch_s = sec / K
     value = pairs / epoch_s
@@ -311,21 +432,43 @@ def run_ours(a):
     nb = (n + a.batch - 1) // a.batch
     alg_bytes_epoch = bytes_per_epoch(a, n, nnz)
     achieved = alg_bytes_epoch / epoch_s / 1e9
+    cap = committed_capture(a, world)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": committed_traffic(a), "kernel": "f2v::force_batch_kernel",
+                "traffic": None, "kernel": "f2v::force_batch_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes_epoch / nb / max(world, 1),
-                "avg_launch_us": epoch_s / nb * 1e6, "peak_source": peak_src}
+                "avg_launch_us": epoch_s / nb * 1e6, "peak_source": peak_src,
+                "frac_algorithmic": achieved / peak, "frac_dram": None, "frac_of_gather_ceiling": None,
+                "note": "frac = algorithmic bytes (every gathered row billed to HBM, SURVEY 8(d)) / time / peak: it exceeds "
+                        "1 where gathered hub rows hit in the 126 MB L2; frac_dram = DRAM bytes ncu measured for this "
+                        "workload and N / time / peak is the utilisation"}
+    if cap:
+        roofline["traffic"] = cap["dram_bytes_per_epoch"] / cap["launches_per_epoch"]
+        roofline["frac_dram"] = cap["dram_bytes_per_epoch"] / epoch_s / 1e9 / peak
+        roofline["traffic_source"] = cap.get("source")
+        roofline["traffic_layout"] = cap.get("layout")
+        if cap.get("gather_ceiling_ms"):
+            roofline["frac_of_gather_ceiling"] = cap["gather_ceiling_ms"] / (epoch_s * 1e3)
 
     # ---- end to end through the host-buffer call
     e2e = None
     if not a.no_e2e:
-        Xin, Xout = X0, torch.empty(X0.shape, dtype=torch.float32, pin_memory=True)   # empty_like would not pin
-        assert Xin.is_pinned() and Xout.is_pinned()
+        if world == 1:
+            Xin = X0
+            Xout = torch.empty((n, a.dim), dtype=torch.float32, pin_memory=True).numpy()   # empty_like would not pin
+            regs = []
+        else:
+            # full-size (virtual) buffers; only this rank's row range is touched and page-locked
+            Xin, Xout = np.empty((n, a.dim), np.float32), np.empty((n, a.dim), np.float32)
+            Xin[lo:hi] = X0[lo:hi]
+            Xout[lo:hi] = 0
+            regs = [Xin[lo:hi], Xout[lo:hi]] if hi > lo else []
+            for r in regs:
+                F.capi.check(F.lib().f2v_host_register(r.ctypes.data, r.nbytes), "f2v_host_register")
         base = W + K
 
         def e2e_step(k):
-            eng.run_epoch_host(a.model, a.batch, a.nsamples, a.bs, a.lr, X_in=Xin.numpy(),
-                               neg=neg_np[(base + k) * stride:(base + k + 1) * stride], X_out=Xout.numpy(), chunk=a.chunk)
+            eng.run_epoch_host(a.model, a.batch, a.nsamples, a.bs, a.lr, X_in=Xin,
+                               neg=neg_np[(base + k) * stride:(base + k + 1) * stride], X_out=Xout, chunk=a.chunk)
         if a.model == 7:
             eng.sample_walks(1, 0)
         for k in range(W):
@@ -344,6 +487,8 @@ def run_ours(a):
             t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_sec = float(t.item())
+        for r in regs:
+            F.lib().f2v_host_unregister(r.ctypes.data)
         # bytes over PCIe per step, whole job: with the peer exchange every rank moves 1/world of the
         # table each way (NCCL mode: every rank moves the whole table)
         tbl = n * a.dim * 4
@@ -357,50 +502,113 @@ def run_ours(a):
 
     cs.__exit__()
     clocks = cs.summary()
+    if world > 1:
+        dist.barrier()                  # nobody unmaps a table a peer may still be storing into
+    eng.close()
+    del eng
 
-    # ---- extra batch sizes (reported, not the headline)
+    # ---- extra lines (N = 1 only; reported, not the headline): the other BASELINE configs that fit
+    # one GPU, the reference's README batch, and the reference's README command through f2v_train
     extra = {}
-    for bsz in [int(x) for x in a.extra_batches.split(",") if x]:
-        b = argparse.Namespace(**vars(a))
-        b.batch = bsz
-        st = host.neg_stream_len(b.model, n, bsz, b.nsamples, b.bs)
-        nn = np.empty(max(4 * st, 1), np.uint32)
-        for k in range(4):
-            g.epoch_negatives(b.model, n, bsz, b.nsamples, b.bs, out=nn[k * st:(k + 1) * st])
-        eng.set_negatives(nn)
-        timed_epochs(torch, dist, eng, b, 2, None, st, 0, world)
-        s2 = timed_epochs(torch, dist, eng, b, 2, None, st, 2, world) / 2
-        extra["B%d" % bsz] = {"epoch_ms": s2 * 1e3, "pairs_per_s": pairs / s2,
-                              "roofline_frac": bytes_per_epoch(b, n, nnz) / s2 / 1e9 / peak}
+    if world == 1 and not a.no_extra:
+        try:
+            extra = extra_lines(torch, F, host, a, peak)
+        except Exception as ex:            # an extra must never cost the headline
+            extra = {"error": repr(ex)}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = cpu_reference(a, rp, ci, 1, warm=False)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = bounded_cpu_baseline(a, host)
 
     if rank == 0:
         line = {"metric": "force_pair_updates_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": epoch_s * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(a), "n": n, "nnz": nnz, "pairs_per_epoch": pairs,
-                           "minibatches_per_epoch": nb, "epoch_mode": a.mode,
-                           "l2": "inputs larger than L2: 2 x %.0f MiB tables + %.0f MiB CSR vs 126 MB L2; no flush needed"
-                                 % (n * a.dim * 4 / 2**20, nnz * 4 / 2**20),
-                           "init": "glibc-compatible srand(1) stream (reference order)",
-                           "parallelism": "replicated table, minibatch split over %d rank(s)%s" %
-                                          (world, "" if world == 1 else (", NCCL all-gather per minibatch" if a.comm == "nccl" else
-                                                      (", row-sharded tables (1/%d of the rows per GPU, remote gathers over NVLink"
-                                                       " + flag barrier per minibatch)" % world) if a.sharded else
-                                                      ", rows stored into the peers' replicas from the force kernel "
-                                                      "(NVLink multicast / peer stores + flag barrier per minibatch)"))},
+                "config": config_of(a, n, nnz),
+                "setup": {"epoch_mode": a.mode, "graph_build_s": round(t_graph, 1),
+                          "l2": "inputs larger than L2: 2 x %.0f MiB tables + %.0f MiB CSR vs 126 MB L2; no flush needed"
+                                % (n * a.dim * 4 / 2**20, nnz * 4 / 2**20),
+                          "init": "glibc-compatible srand(1) stream (reference order)",
+                          "device_memory_used_GiB": round((total_b - free_b) / 2**30, 1),
+                          "parallelism": "replicated table, minibatch split over %d rank(s)%s" %
+                                         (world, "" if world == 1 else (", NCCL all-gather per minibatch" if a.comm == "nccl" else
+                                                     (", row-sharded tables (1/%d of the rows per GPU, remote gathers over NVLink"
+                                                      " + flag barrier per minibatch)" % world) if a.sharded else
+                                                     ", rows stored into the peers' replicas from the force kernel "
+                                                     "(NVLink multicast / peer stores + flag barrier per minibatch)"))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "epoch_s": epoch_s, "extra": extra}
+                "cpu_baseline": cpu, "epoch_s": epoch_s, "parity": parity, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()                  # nobody unmaps a table a peer may still be storing into
-    eng.close()
-    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def quick_epochs(torch, eng, a, host, g, n, epochs=3):
+    """best-of epoch time (ms) of a resident workload (engine's own events)."""
+    st = host.neg_stream_len(a.model, n, a.batch, a.nsamples, a.bs)
+    neg = g.epoch_negatives(a.model, n, a.batch, a.nsamples, a.bs).copy()
+    eng.set_negatives(neg)
+    ms = []
+    for k in range(epochs):
+        eng.set_negative_offset(0)
+        if a.model == 7:
+            eng.sample_walks(1, k)
+        eng.run_epoch(a.model, a.batch, a.nsamples, a.bs, a.lr, a.chunk)
+        ms.append(eng.last_epoch_ms())
+    return min(ms[1:]) if len(ms) > 1 else ms[0], st
+
+
+def extra_lines(torch, F, host, a, peak):
+    out = {}
+    for name in ("cfg2", "cfg3"):
+        if name == a.workload:
+            continue
+        b = argparse.Namespace(**vars(a))
+        for k, v in WORKLOADS[name].items():
+            setattr(b, k, v)
+        rp, ci = host.rmat_csr_cached(b.scale, b.edge_factor, 1)
+        n, nnz = len(rp) - 1, len(ci)
+        g = host.RandStream(1)
+        X0 = g.init_embeddings(b.model, n, b.dim)
+        with make_engine(F, b, rp, ci, torch.cuda.current_device()) as eng:
+            eng.set_embeddings(X0)
+            batches = [b.batch] + ([256] if name == "cfg2" else [])
+            for bsz in batches:
+                b.batch = bsz
+                ms, _ = quick_epochs(torch, eng, b, host, g, n, 4 if bsz >= 4096 else 2)
+                key = name if bsz == WORKLOADS[name]["batch"] else "%s_B%d" % (name, bsz)
+                out[key] = {"workload": workload_name(b), "epoch_ms": ms, "pairs_per_s": pairs_per_epoch(b, n, nnz) / ms * 1e3,
+                            "frac_algorithmic": bytes_per_epoch(b, n, nnz) / ms / 1e6 / peak}
+    # cfg1: the reference's README command (cora, option 5, d=128, batch 256, 1200 iterations) through the
+    # whole-run driver f2v_train (init + epochs + download, the span the reference itself times)
+    mtx = os.path.join(ROOT, "tests", "golden", "cora.mtx")
+    if os.path.exists(mtx):
+        rp, ci = host.load_mtx(mtx)
+        alg = F.Algorithms(rp, ci, "cora.mtx", "/tmp/", 128)
+        alg.AlgoForce2VecNS(50, 0, 256, 5, 0.02, write=False)            # warm-up (context, plan)
+        sec = alg.AlgoForce2VecNS(1200, 0, 256, 5, 0.02, write=False)[0]
+        n, nnz = len(rp) - 1, len(ci)
+        out["cfg1_cora_B256_it1200"] = {"workload": "cora.mtx option5 d128 B256 it1200 s5 (README.md:44) via f2v_train",
+                                        "wall_s": sec, "pairs_per_s": (nnz + 5 * n) * 1200 / sec,
+                                        "reference_wall_s_survey_8vcpu": 3.81}
+    return out
+
+
+def bounded_cpu_baseline(a, host):
+    """cpu_baseline: the unmodified reference on this box's cores, on a BOUNDED sample of the workload --
+    the same option / bs / dim / batch on the R-MAT graph of the same family with at most 2^20 vertices
+    (one epoch; ~10-30 s of CPU work), in pair updates / s."""
+    b = argparse.Namespace(**vars(a))
+    b.scale = min(a.scale, 20)
+    b.batch = min(a.batch, 1 << b.scale)
+    rp, ci = host.rmat_csr_cached(b.scale, b.edge_factor, 1)
+    r = cpu_reference(b, rp, ci, 1, warm=False)
+    return {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": "one epoch of %s (%s, %d threads, init differenced out)%s" %
+                      (workload_name(b), r["what"], r["cores"],
+                       "" if b.scale == a.scale else "; the R-MAT-%d graph of the same generator stands in for R-MAT-%d: "
+                       "a full epoch of the headline workload on the CPU is what `--impl reference` times" % (b.scale, a.scale))}
 
 
 def main():

@@ -16,6 +16,7 @@ ENGINE_SYMBOLS = [
     "f2v_get_walks", "f2v_sample_walks", "f2v_step", "f2v_run_epoch", "f2v_run_epoch_host",
     "f2v_set_epoch_mode", "f2v_set_option", "f2v_launch_count", "f2v_last_epoch_ms", "f2v_comm_unique_id",
     "f2v_comm_init", "f2v_comm_peer_export", "f2v_comm_peer_init", "f2v_trace_ms", "f2v_shard_row",
+    "f2v_checksum", "f2v_host_register", "f2v_host_unregister", "f2v_device_memory",
 ]
 HOST_SYMBOLS = [
     "f2v_rng_create", "f2v_rng_destroy", "f2v_rng_next", "f2v_init_embeddings", "f2v_build_lut",
@@ -61,6 +62,10 @@ def lib():
     L.f2v_sync.argtypes = [vp]
     L.f2v_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.f2v_host_free.argtypes = [vp]
+    L.f2v_host_register.argtypes = [vp, u64]
+    L.f2v_host_unregister.argtypes = [vp]
+    L.f2v_device_memory.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.f2v_checksum.argtypes = [vp, C.POINTER(u64)]
     L.f2v_set_embeddings.argtypes = [vp, vp]
     L.f2v_get_embeddings.argtypes = [vp, vp]
     L.f2v_get_rows.argtypes = [vp, u64, u64, vp]

@@ -32,6 +32,16 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+// the host side of the library (f2v_host.cpp) reports through the same per-thread message
+namespace f2v {
+int host_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace f2v
 #define CU(call)                                                                              \
     do {                                                                                      \
         cudaError_t _e = (call);                                                              \
@@ -172,6 +182,14 @@ static int sock_byte(int sock, bool send_it, char b) {
     char got = 0;
     return (recv(sock, &got, 1, MSG_WAITALL) == 1 && got == b) ? 0 : -1;
 }
+// The hand-off must never block for ever: a rank that failed (or died) before its handshake would
+// otherwise leave every peer in accept()/recv().  Receive and send time-outs turn that into an error.
+static void sock_timeouts(int fd, int seconds) {
+    struct timeval tv = {seconds, 0};
+    setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));     // also bounds accept() on a listening socket
+    setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
+}
+constexpr int kHandoffTimeoutS = 120;
 static void sock_addr(struct sockaddr_un* a, socklen_t* len, const char* name) {
     memset(a, 0, sizeof(*a));
     a->sun_family = AF_UNIX;
@@ -182,7 +200,7 @@ static void sock_addr(struct sockaddr_un* a, socklen_t* len, const char* name) {
 
 // ------------------------------------------------------------------ engine -------------
 struct Plan {
-    uint32_t batch = 0, chunk = 0, par = 0;
+    uint32_t batch = 0, chunk = 0, par = 0, min_chunk = 0;
     bool walk = false;
     int rank = 0, world = 1, assign = 0;
     uint64_t first_row = 0, nrows = 0;      // row range covered (whole table for epochs)
@@ -228,7 +246,8 @@ struct f2v_engine {
     int epoch_mode = 0;
     int variant = -1;                        // d=128 lane layout: -1 auto, see launch_batch
     int neg_smem = 1;
-    int persist = 0;                         // 1: persistent CTAs striding over the item list (measured slower)
+    int epoch_ctas = 0;                      // persistent epoch kernel: CTAs per SM (0 = as many as fit)
+    uint32_t min_chunk = 0;                  // lower bound of the adaptive hub chunk (0 = default_min_chunk(batch))
     int par = 9472;                          // adaptive-chunk target: 148 SMs x 64 lane groups (0 = fixed chunk)
     uint64_t launches = 0;
     int rank = 0, world = 1;
@@ -271,8 +290,10 @@ struct f2v_engine {
     int order = -1;                          // item order after the hub chunks: 0 descending degree, 1 light rows first,
                                              // 2 light rows interleaved; -1 = default (0 on one GPU, 1 on several)
     int pdl = 2;                             // programmatic dependent launch of consecutive minibatches (0 off, 1, 2)
-    int peer_sig = 1;                        // 1: a 1-CTA kernel after the force kernel publishes the step (default);
-                                             // 0: the force kernel's last CTA does (a system fence per CTA: measured slower)
+    int peer_sig = 2;                        // who publishes a minibatch's exchange step: 2 (default) = CTA 0 of the NEXT
+                                             // launch, after its dependency wait (launches stay PDL-chained); 1 = a 1-CTA
+                                             // kernel after the force kernel; 0 = the force kernel's last CTA (a system
+                                             // fence per CTA: measured slower)
 };
 
 // What a rank publishes for the peer-store exchange (f2v_comm_peer_export): fits F2V_PEER_BLOB.
@@ -333,11 +354,12 @@ static int ensure_tables(f2v_engine* e) {
 // hub-row partial buffers.  Cached on (batch, chunk, walk, rank, world, range).
 static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrows, uint32_t batch,
                       uint32_t chunk, uint32_t par, bool walk, int rank, int world, int assign) {
-    if (pl.d_items && pl.batch == batch && pl.chunk == chunk && pl.par == par && pl.walk == walk && pl.rank == rank &&
+    if (pl.d_items && pl.batch == batch && pl.chunk == chunk && pl.par == par && pl.min_chunk == e->min_chunk &&
+        pl.walk == walk && pl.rank == rank &&
         pl.world == world && pl.assign == assign && pl.first_row == first_row && pl.nrows == nrows)
         return F2V_OK;
     HostPlan hp;
-    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, par, walk, rank, world, assign, hp);
+    build_host_plan(e->h_rowptr.data(), first_row, nrows, batch, chunk, par, walk, rank, world, assign, hp, e->min_chunk);
     const uint64_t nb = hp.nb, total = hp.items.size();
     std::vector<Item>& items = hp.items;
     std::vector<HubInfo>& hub = hp.hub;
@@ -378,7 +400,7 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         CU(cudaMemsetAsync(e->d_counters, 0, sizeof(uint32_t) * slots, e->stream));
         e->slots_cap = slots;
     }
-    pl.batch = batch; pl.chunk = chunk; pl.par = par; pl.walk = walk; pl.rank = rank; pl.world = world;
+    pl.batch = batch; pl.chunk = chunk; pl.par = par; pl.min_chunk = e->min_chunk; pl.walk = walk; pl.rank = rank; pl.world = world;
     pl.assign = assign;
     pl.first_row = first_row; pl.nrows = nrows; pl.nb = nb;
     pl.item_ptr.swap(item_ptr);
@@ -395,7 +417,17 @@ static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_
     const bool negs = L::kBulk && p.neg_in_smem;
     const bool lut_s = PERSIST && MODEL != kTDist && L::kBulk;
     size_t smem = 0;
-    if (negs || lut_s) smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0) + (lut_s ? kLutAlloc * sizeof(float) : 0);
+    if (negs || lut_s || L::kStages > 0)
+        smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0) + (lut_s ? kLutAlloc * sizeof(float) : 0);
+    if constexpr (L::kStages > 0) {
+        smem += L::kCtaBytes;                        // the lane groups' asynchronous-copy rings
+        static bool carve = false;                   // (per instantiation) all of the SM's L1/shared array as shared
+        if (!carve) {                                // memory: rows bypass L1, MINB CTAs of ring must fit
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            carve = true;
+        }
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -423,25 +455,22 @@ static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_
 }
 
 template <class L, int MODEL>
-static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
-    // (the per-minibatch kernel with persistent CTAs was measured slower and is no longer instantiated;
-    // the persistent variant that remains is the one-launch-per-epoch kernel, epoch mode 1)
-    (void)persist;
+static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st, int sm_count) {
     return launch_batch_k<L, MODEL, false>(p, st, sm_count);
 }
 
 template <class L>
-static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
+static cudaError_t launch_batch_m(int model, const BatchParams& p, cudaStream_t st, int sm_count) {
     switch (model) {
-    case kTDist: return launch_batch_t<L, kTDist>(p, st, sm_count, persist);
-    case kSigmoid: return launch_batch_t<L, kSigmoid>(p, st, sm_count, persist);
-    default: return launch_batch_t<L, kWalk>(p, st, sm_count, persist);
+    case kTDist: return launch_batch_t<L, kTDist>(p, st, sm_count);
+    case kSigmoid: return launch_batch_t<L, kSigmoid>(p, st, sm_count);
+    default: return launch_batch_t<L, kWalk>(p, st, sm_count);
     }
 }
 
-static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st, int sm_count, int persist) {
+static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st, int sm_count) {
     switch (p.dim) {
-    case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st, sm_count, persist);
+    case 32: return launch_batch_m<VecL<32, 8, 8>>(model, p, st, sm_count);
     case 64:
         // auto (-1): small launches run 4 rows in flight per 8-lane group (104 registers: latency-bound);
         // large ones 2 rows in flight at 64 registers / 4 CTAs per SM, the walk model (every item has
@@ -449,9 +478,12 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         // option 7 2.42 -> 1.46 ms, option 6 1.41 -> 1.22 ms per epoch at batch 65536
         // (batch 16384, option 7: 2.82 / 1.90 / 2.09 ms for the three layouts; batch 4096: 5.76 / 6.72 / 7.03)
         switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u && model == kWalk ? 4 : (p.n_items >= 8000u ? 1 : 0))) {
-        case 1: return launch_batch_m<VecL<64, 8, 2, 4>>(model, p, st, sm_count, persist);
-        case 4: return launch_batch_m<VecL<64, 8, 2, 5>>(model, p, st, sm_count, persist);
-        default: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count, persist);
+        case 20: return launch_batch_m<RingL<64, 8, 2, 5>>(model, p, st, sm_count);
+        case 21: return launch_batch_m<RingL<64, 8, 3, 4>>(model, p, st, sm_count);
+        case 22: return launch_batch_m<RingL<64, 8, 4, 3>>(model, p, st, sm_count);
+        case 1: return launch_batch_m<VecL<64, 8, 2, 4>>(model, p, st, sm_count);
+        case 4: return launch_batch_m<VecL<64, 8, 2, 5>>(model, p, st, sm_count);
+        default: return launch_batch_m<VecL<64, 8, 4>>(model, p, st, sm_count);
         }
     case 128:
         // auto (-1): 4 CTAs/SM at 64 registers; launches with many items run 5 CTAs/SM at 48 registers
@@ -459,26 +491,29 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         // slower below); small launches are latency-bound, not occupancy-bound, and run 8 rows in
         // flight per group at 128 registers (5-11 % faster below ~12 K items)
         switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u ? 8 : (p.n_items < 12000u ? 11 : 3))) {
-        case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count, persist);
-        case 8: return launch_batch_m<VecL<128, 16, 2, 5>>(model, p, st, sm_count, persist);
-        case 11: return launch_batch_m<VecL<128, 16, 8, 2>>(model, p, st, sm_count, persist);
-        default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st, sm_count, persist);   // 3
+        case 20: return launch_batch_m<RingL<128, 16, 2, 5>>(model, p, st, sm_count);
+        case 21: return launch_batch_m<RingL<128, 16, 3, 4>>(model, p, st, sm_count);
+        case 22: return launch_batch_m<RingL<128, 16, 4, 3>>(model, p, st, sm_count);
+        case 23: return launch_batch_m<RingL<128, 16, 2, 4>>(model, p, st, sm_count);
+        case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count);
+        case 8: return launch_batch_m<VecL<128, 16, 2, 5>>(model, p, st, sm_count);
+        case 11: return launch_batch_m<VecL<128, 16, 8, 2>>(model, p, st, sm_count);
+        default: return launch_batch_m<VecL<128, 16, 2, 4>>(model, p, st, sm_count);   // 3
         }
-    case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st, sm_count, persist);
+    case 256: return launch_batch_m<VecL<256, 32, 4>>(model, p, st, sm_count);
     default: break;
     }
-    if (p.dim <= 32) return launch_batch_m<GenL<1>>(model, p, st, sm_count, persist);
-    if (p.dim <= 64) return launch_batch_m<GenL<2>>(model, p, st, sm_count, persist);
-    if (p.dim <= 128) return launch_batch_m<GenL<4>>(model, p, st, sm_count, persist);
-    if (p.dim <= 256) return launch_batch_m<GenL<8>>(model, p, st, sm_count, persist);
-    if (p.dim <= 512) return launch_batch_m<GenL<16>>(model, p, st, sm_count, persist);
-    return launch_batch_m<GenL<32>>(model, p, st, sm_count, persist);
+    if (p.dim <= 32) return launch_batch_m<GenL<1>>(model, p, st, sm_count);
+    if (p.dim <= 64) return launch_batch_m<GenL<2>>(model, p, st, sm_count);
+    if (p.dim <= 128) return launch_batch_m<GenL<4>>(model, p, st, sm_count);
+    if (p.dim <= 256) return launch_batch_m<GenL<8>>(model, p, st, sm_count);
+    if (p.dim <= 512) return launch_batch_m<GenL<16>>(model, p, st, sm_count);
+    return launch_batch_m<GenL<32>>(model, p, st, sm_count);
 }
 
 // ---- persistent epoch kernel (epoch mode 1): cooperative launch, grid = SMs x resident CTAs
-static int g_epoch_ctas_per_sm = 0;     // 0 = as many as fit (tuning knob "epoch_ctas")
 template <class L, int MODEL>
-static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid_out, bool query) {
+static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm_count, int ctas_per_sm, unsigned* grid_out, bool query) {
     auto kern = force_epoch_kernel<L, MODEL>;
     const BatchParams& p = ep.p;
     const bool negs = L::kBulk && p.neg_in_smem;
@@ -493,7 +528,7 @@ static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    if (g_epoch_ctas_per_sm > 0) per_sm = std::min(per_sm, g_epoch_ctas_per_sm);
+    if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
     const unsigned grid = (unsigned)(sm_count * per_sm);
     *grid_out = grid;
     if (query) return cudaSuccess;
@@ -502,29 +537,29 @@ static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm
 }
 
 template <class L>
-static cudaError_t launch_epoch_m(int model, const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid, bool query) {
+static cudaError_t launch_epoch_m(int model, const EpochParams& ep, cudaStream_t st, int sm_count, int cps, unsigned* grid, bool query) {
     switch (model) {
-    case kTDist: return launch_epoch_k<L, kTDist>(ep, st, sm_count, grid, query);
-    case kSigmoid: return launch_epoch_k<L, kSigmoid>(ep, st, sm_count, grid, query);
-    default: return launch_epoch_k<L, kWalk>(ep, st, sm_count, grid, query);
+    case kTDist: return launch_epoch_k<L, kTDist>(ep, st, sm_count, cps, grid, query);
+    case kSigmoid: return launch_epoch_k<L, kSigmoid>(ep, st, sm_count, cps, grid, query);
+    default: return launch_epoch_k<L, kWalk>(ep, st, sm_count, cps, grid, query);
     }
 }
 
-static cudaError_t launch_epoch(int model, const EpochParams& ep, cudaStream_t st, int sm_count, unsigned* grid, bool query) {
+static cudaError_t launch_epoch(int model, const EpochParams& ep, cudaStream_t st, int sm_count, int cps, unsigned* grid, bool query) {
     const uint32_t dim = ep.p.dim;
     switch (dim) {
-    case 32: return launch_epoch_m<VecL<32, 8, 8>>(model, ep, st, sm_count, grid, query);
-    case 64: return launch_epoch_m<VecL<64, 8, 4>>(model, ep, st, sm_count, grid, query);
-    case 128: return launch_epoch_m<VecL<128, 16, 2, 4>>(model, ep, st, sm_count, grid, query);
-    case 256: return launch_epoch_m<VecL<256, 32, 4>>(model, ep, st, sm_count, grid, query);
+    case 32: return launch_epoch_m<VecL<32, 8, 8>>(model, ep, st, sm_count, cps, grid, query);
+    case 64: return launch_epoch_m<VecL<64, 8, 4>>(model, ep, st, sm_count, cps, grid, query);
+    case 128: return launch_epoch_m<VecL<128, 16, 2, 4>>(model, ep, st, sm_count, cps, grid, query);
+    case 256: return launch_epoch_m<VecL<256, 32, 4>>(model, ep, st, sm_count, cps, grid, query);
     default: break;
     }
-    if (dim <= 32) return launch_epoch_m<GenL<1>>(model, ep, st, sm_count, grid, query);
-    if (dim <= 64) return launch_epoch_m<GenL<2>>(model, ep, st, sm_count, grid, query);
-    if (dim <= 128) return launch_epoch_m<GenL<4>>(model, ep, st, sm_count, grid, query);
-    if (dim <= 256) return launch_epoch_m<GenL<8>>(model, ep, st, sm_count, grid, query);
-    if (dim <= 512) return launch_epoch_m<GenL<16>>(model, ep, st, sm_count, grid, query);
-    return launch_epoch_m<GenL<32>>(model, ep, st, sm_count, grid, query);
+    if (dim <= 32) return launch_epoch_m<GenL<1>>(model, ep, st, sm_count, cps, grid, query);
+    if (dim <= 64) return launch_epoch_m<GenL<2>>(model, ep, st, sm_count, cps, grid, query);
+    if (dim <= 128) return launch_epoch_m<GenL<4>>(model, ep, st, sm_count, cps, grid, query);
+    if (dim <= 256) return launch_epoch_m<GenL<8>>(model, ep, st, sm_count, cps, grid, query);
+    if (dim <= 512) return launch_epoch_m<GenL<16>>(model, ep, st, sm_count, cps, grid, query);
+    return launch_epoch_m<GenL<32>>(model, ep, st, sm_count, cps, grid, query);
 }
 
 static bool bulk_ok(const f2v_engine* e, uint32_t s, int bs_mode) {
@@ -639,25 +674,38 @@ int f2v_create(f2v_engine** out, int device_id, uint64_t n, uint64_t nnz, const 
     f2v_engine* e = new (std::nothrow) f2v_engine();
     if (!e) return fail(F2V_ERR_NOMEM, "out of host memory");
     e->device = device_id; e->n = n; e->nnz = nnz; e->dim = dim;
-    e->h_rowptr.assign(rowptr, rowptr + n + 1);
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device_id));
-    e->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) { delete e; return fail(F2V_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); }
-    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-    e->stream = e->own_stream;
-    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&e->ev_rows, cudaEventDisableTiming));
-    CU(cudaEventCreate(&e->ev0));
-    CU(cudaEventCreate(&e->ev1));
-    CU(cudaMalloc((void**)&e->d_rowptr, sizeof(uint64_t) * (n + 1)));
-    CU(cudaMalloc((void**)&e->d_colids, sizeof(uint32_t) * (nnz ? nnz : 1)));
-    CU(cudaMemcpyAsync(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, e->stream));
-    if (nnz) CU(cudaMemcpyAsync(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    e->rows_alloc = n;                       // tables are allocated on first use (ensure_tables): a row-sharded
-                                             // engine never holds a full-size table
-    CU(cudaMalloc((void**)&e->d_lut, sizeof(float) * kLutAlloc));
+    // everything below can fail (out of device memory on a large graph): one exit path releases
+    // what was created so far (f2v_destroy accepts a partly built engine)
+    int rc = [&]() -> int {
+        try { e->h_rowptr.assign(rowptr, rowptr + n + 1); } catch (const std::bad_alloc&) { return fail(F2V_ERR_NOMEM, "out of host memory"); }
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device_id));
+        e->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) return fail(F2V_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+        CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+        e->stream = e->own_stream;
+        CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->ev_rows, cudaEventDisableTiming));
+        CU(cudaEventCreate(&e->ev0));
+        CU(cudaEventCreate(&e->ev1));
+        CU(cudaMalloc((void**)&e->d_rowptr, sizeof(uint64_t) * (n + 1)));
+        CU(cudaMalloc((void**)&e->d_colids, sizeof(uint32_t) * (nnz ? nnz : 1)));
+        CU(cudaMemcpyAsync(e->d_rowptr, rowptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, e->stream));
+        if (nnz) CU(cudaMemcpyAsync(e->d_colids, colids, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        e->rows_alloc = n;                       // tables are allocated on first use (ensure_tables): a row-sharded
+                                                 // engine never holds a full-size table
+        CU(cudaMalloc((void**)&e->d_lut, sizeof(float) * kLutAlloc));
+        return F2V_OK;
+    }();
+    if (rc != F2V_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));       // f2v_destroy must not clobber the message
+        f2v_destroy(e);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
     *out = e;
     return F2V_OK;
 }
@@ -720,6 +768,27 @@ int f2v_host_alloc(void** p, uint64_t bytes) {
 
 int f2v_host_free(void* p) {
     if (p) CU(cudaFreeHost(p));
+    return F2V_OK;
+}
+
+int f2v_host_register(void* p, uint64_t bytes) {
+    if (!p || !bytes) return fail(F2V_ERR_ARG, "null argument");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return F2V_OK;
+}
+
+int f2v_host_unregister(void* p) {
+    if (p) CU(cudaHostUnregister(p));
+    return F2V_OK;
+}
+
+int f2v_device_memory(const f2v_engine* e, uint64_t* free_bytes, uint64_t* total_bytes) {
+    if (!e) return fail(F2V_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
     return F2V_OK;
 }
 
@@ -788,6 +857,35 @@ int f2v_get_rows(f2v_engine* e, uint64_t first_row, uint64_t nrows, float* rows)
                        cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return F2V_OK;
+}
+
+int f2v_checksum(f2v_engine* e, uint64_t* out) {
+    if (!e || !out) return fail(F2V_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    { int r = e->shard_mode ? F2V_OK : ensure_tables(e); if (r) return r; }
+    if (e->shard_mode && e->step_id) {
+        // other ranks' shards are read: every rank must have published the current exchange step
+        BatchParams p{};
+        p.n_peers = (uint32_t)(e->world - 1);
+        p.rank = (uint32_t)e->rank; p.world = (uint32_t)e->world;
+        p.flags = e->d_flags; p.done = e->d_done;
+        p.timeout_ns = (uint64_t)e->exchange_timeout_ms * 1000000ull; p.timed_out = e->d_done + 1;
+        p.wait_step = e->step_id;
+        peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    unsigned long long* d_sum = nullptr;
+    CU(cudaMalloc((void**)&d_sum, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), e->stream));
+    checksum_kernel<<<(unsigned)e->sm_count * 8, 256, 0, e->stream>>>(e->d_X[e->cur], e->n, e->dim, e->shard_lg, e->shard_rows, d_sum);
+    cudaError_t le = cudaGetLastError();
+    unsigned long long h = 0;
+    if (le == cudaSuccess) le = cudaMemcpyAsync(&h, d_sum, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
+    cudaFree(d_sum);
+    if (le != cudaSuccess) return fail(F2V_ERR_CUDA, "f2v_checksum: %s", cudaGetErrorString(le));
+    *out = (uint64_t)h;
+    return check_exchange(e);
 }
 
 int f2v_set_lut(f2v_engine* e, const float* t, uint32_t count) {
@@ -895,7 +993,7 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows, const
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
     p.lr = lr; p.variant = e->variant;
-    CU(launch_batch(model, p, e->stream, e->sm_count, e->persist));
+    CU(launch_batch(model, p, e->stream, e->sm_count));
     e->launches++;
     // apply after the join (algorithms.cpp:629-639 / :913-921)
     CU(cudaMemcpyAsync(e->d_X[e->cur] + first_row * e->dim, e->d_stage, sizeof(float) * (uint64_t)nrows * e->dim,
@@ -939,14 +1037,12 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
                    (e->peer_mode ? kAssignBalanced : kAssignSlices) | (order == 1 ? kOrderLightFirst : 0) | (order == 2 ? kOrderInterleave : 0));
     if (r) return r;
     const Plan& pl = e->epoch_plan;
-    float* Xold = e->d_X[e->cur];
     float* Xnew = e->d_X[1 - e->cur];
     CU(cudaEventRecord(e->ev0, e->stream));
     BatchParams p{};
     p.Xb = e->d_Xall; p.out = Xnew; p.out_base = 0;
     p.off_lo = (uint32_t)((uint64_t)(1 - e->cur) * e->rows_alloc);      // rows already updated this epoch: next table
     p.off_hi = (uint32_t)((uint64_t)e->cur * e->rows_alloc);            // the others: current table
-    (void)Xold;
     p.colids = e->d_colids; p.walks = e->d_walks; p.lut = e->d_lut;
     p.partials = e->d_partials; p.counters = e->d_counters;
     p.s = s; p.dim = e->dim; p.bs_mode = bs_mode; p.neg_in_smem = bulk_ok(e, s, bs_mode) ? 1 : 0;
@@ -980,12 +1076,12 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         ep.item_ptr = pl.d_item_ptr; ep.nb = (uint32_t)nb; ep.batch = batch; ep.neg_stride = (uint32_t)W;
         ep.step0 = e->step_id;
         unsigned grid = 0;
-        CU(launch_epoch(model, ep, e->stream, e->sm_count, &grid, true));
+        CU(launch_epoch(model, ep, e->stream, e->sm_count, e->epoch_ctas, &grid, true));
         if ((uint64_t)grid * nb < 0xffffffffull) {
             if (!e->d_bar) CU(cudaMalloc((void**)&e->d_bar, 128));
             CU(cudaMemsetAsync(e->d_bar, 0, 128, e->stream));
             ep.bar_count = e->d_bar;
-            CU(launch_epoch(model, ep, e->stream, e->sm_count, &grid, false));
+            CU(launch_epoch(model, ep, e->stream, e->sm_count, e->epoch_ctas, &grid, false));
             e->launches++;
             if (e->peer_mode) e->step_id += nb;
             if (X_out_host)
@@ -1002,6 +1098,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         CU(cudaEventRecord(e->trace_ev[0], e->stream));
         e->trace_n = nb;
     }
+    bool first_launch = true;
     for (uint64_t b = 0; b < nb; b++) {
         p.items = pl.d_items + pl.item_ptr[b];
         p.hub = pl.d_hub + pl.item_ptr[b];
@@ -1012,17 +1109,35 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         p.neg = e->d_neg + e->neg_off + b * W;
         // the epoch's first launch is an ordinary one: it follows host copies (negatives, walks, the
         // table) and must see a freshly invalidated L1; launches 1.. are programmatic dependents
-        p.pdl = (e->pdl && e->world == 1 && b >= 1) ? (e->pdl >= 2 ? 2 : 1) : 0;
+        // (multi-GPU with the NCCL all-gather: a collective sits between two launches, no chaining)
+        const bool chain = e->pdl && (e->world == 1 || (e->peer_mode && e->peer_sig == 2)) && !first_launch;
+        p.pdl = chain ? (e->pdl >= 2 ? 2 : 1) : 0;
         if (e->peer_mode) {
             // minibatch b reads rows its peers stored during step_id (minibatch b-1); it publishes step_id+1
             p.wait_step = (e->peer_debug & 2) ? 0 : e->step_id;
             p.signal_step = ++e->step_id;
         }
-        if (p.n_items) {
+        if (e->peer_mode && e->peer_sig == 2) {
+            // "successor publishes": this launch's CTA 0 publishes the PREVIOUS minibatch's step once the
+            // previous launch is complete (stream order or griddepcontrol.wait -- the kernel boundary has
+            // performed its peer stores), every warp waits for the peers' flags after its own dependency
+            // wait.  One launch per minibatch, no system-scope fence per CTA.  A minibatch with no rows
+            // on this rank launches nothing: its step is implied by the next publication (flags are
+            // monotone).
+            p.publish_step = p.wait_step;
+            p.signal_step = 0;
+            p.late_wait = 1;
+            if (p.n_items) {
+                CU(launch_batch(model, p, e->stream, e->sm_count));
+                e->launches++;
+                first_launch = false;
+            }
+        } else if (p.n_items) {
             const uint64_t sig = p.signal_step;
             if (e->peer_mode && e->peer_sig) p.signal_step = 0;
-            CU(launch_batch(model, p, e->stream, e->sm_count, e->persist));
+            CU(launch_batch(model, p, e->stream, e->sm_count));
             e->launches++;
+            first_launch = false;
             if (e->peer_mode && e->peer_sig && p.n_peers) {
                 // the force kernel has drained (all its peer stores are performed): publish the step
                 BatchParams q = p;
@@ -1056,9 +1171,13 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         }
     }
     if (e->peer_mode) {
-        // the replica is complete once every peer has published the epoch's last step
+        // the replica is complete once every peer has published the epoch's last step (this rank's own
+        // last step is published here when the successor-publishes scheme is on: the last force launch
+        // is complete in stream order)
         p.wait_step = (e->peer_debug & 2) ? 0 : e->step_id;
         p.signal_step = 0;
+        p.publish_step = e->peer_sig == 2 ? e->step_id : 0;
+        p.late_wait = 0; p.pdl = 0;
         peer_sync_kernel<<<1, 32, 0, e->stream>>>(p);
         CU(cudaGetLastError());
         e->launches++;
@@ -1153,8 +1272,6 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     if (!strcmp(name, "variant")) e->variant = (int)value;
     else if (!strcmp(name, "neg_smem")) e->neg_smem = value != 0;
     else if (!strcmp(name, "par")) e->par = (int)value;
-    else if (!strcmp(name, "prefetch")) { (void)value; }   // L2 prefetch variants were measured (no gain) and removed
-    else if (!strcmp(name, "persist")) { (void)value; }    // removed: see launch_batch_t
     else if (!strcmp(name, "peer_debug")) e->peer_debug = (int)value;
     else if (!strcmp(name, "peer_sig")) e->peer_sig = (int)value;
     else if (!strcmp(name, "pdl")) e->pdl = (int)value;
@@ -1163,8 +1280,8 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "trace")) e->trace = (int)value;
     else if (!strcmp(name, "exchange_timeout_ms")) e->exchange_timeout_ms = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "sharded")) e->want_shard = value != 0;
-    else if (!strcmp(name, "epoch_ctas")) g_epoch_ctas_per_sm = (int)value;
-    else if (!strcmp(name, "min_chunk")) { min_chunk_override() = (uint32_t)std::max<int64_t>(0, value); e->epoch_plan.batch = 0; e->step_plan.batch = 0; }
+    else if (!strcmp(name, "epoch_ctas")) e->epoch_ctas = (int)value;
+    else if (!strcmp(name, "min_chunk")) e->min_chunk = (uint32_t)std::max<int64_t>(0, value);   // part of the plan cache key
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;
 }
@@ -1259,6 +1376,7 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
                 struct sockaddr_un a;
                 socklen_t alen;
                 sock_addr(&a, &alen, e->sock_name);
+                if (s >= 0) sock_timeouts(s, kHandoffTimeoutS);
                 if (s >= 0 && bind(s, (struct sockaddr*)&a, alen) == 0 && listen(s, kMaxWorld) == 0) e->listen_sock = s;
                 else if (s >= 0) close(s);
             }
@@ -1320,6 +1438,7 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
         }
         for (int k = 1; k < world; k++) {
             int c = accept(e->listen_sock, nullptr, nullptr);
+            if (c >= 0) sock_timeouts(c, kHandoffTimeoutS);
             char who = 0;
             if (c < 0 || recv(c, &who, 1, MSG_WAITALL) != 1 || who < 1 || who >= world || conns[(int)who] >= 0) {
                 if (c >= 0) close(c);
@@ -1336,6 +1455,7 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
         close(fd);
     } else {
         int c = socket(AF_UNIX, SOCK_STREAM, 0);
+        if (c >= 0) sock_timeouts(c, kHandoffTimeoutS);
         struct sockaddr_un a;
         socklen_t alen;
         sock_addr(&a, &alen, blobs[0].sock_name);
@@ -1368,26 +1488,47 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
         if (sock_byte(conns[0], true, tag)) return -1;
         return sock_byte(conns[0], false, (char)(tag + 1));
     };
-    DRV(g_drv.MulticastAddDevice(mc, dev));
-    if (handshake('A')) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: add-device handshake failed"); }
+    // from here on a local failure must not leave the peers waiting in a handshake or leak the
+    // handles: everything acquired is tracked and released on the error path, the sockets are closed
+    // (the peers' next handshake byte then fails at once instead of after the time-out)
     CUmemGenericAllocationHandle mem = 0;
-    DRV(g_drv.MemCreate(&mem, size, &ap, 0));
-    DRV(g_drv.MulticastBindMem(mc, 0, mem, 0, size, 0));
-    CUmemAccessDesc ad;
-    memset(&ad, 0, sizeof(ad));
-    ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = e->device; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
     CUdeviceptr uc = 0, mcva = 0;
-    DRV(g_drv.MemAddressReserve(&uc, size, gran, 0, 0));
-    DRV(g_drv.MemMap(uc, size, 0, mem, 0));
-    DRV(g_drv.MemSetAccess(uc, size, &ad, 1));
-    DRV(g_drv.MemAddressReserve(&mcva, size, gran, 0, 0));
-    DRV(g_drv.MemMap(mcva, size, 0, mc, 0));
-    DRV(g_drv.MemSetAccess(mcva, size, &ad, 1));
-    // move the live state over (through the unicast mapping) and drop the cudaMalloc'ed tables
-    CU(cudaMemsetAsync((void*)uc, 0, size, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    CU(cudaMemcpyAsync((void*)uc, e->d_Xall, 2 * tbl, cudaMemcpyDeviceToDevice, e->stream));
-    CU(cudaDeviceSynchronize());
+    bool uc_mapped = false, mc_mapped = false, bound = false;
+    int rr = [&]() -> int {
+        DRV(g_drv.MulticastAddDevice(mc, dev));
+        if (handshake('A')) return fail(F2V_ERR_STATE, "multicast hand-off: add-device handshake failed (a peer gave up?)");
+        DRV(g_drv.MemCreate(&mem, size, &ap, 0));
+        DRV(g_drv.MulticastBindMem(mc, 0, mem, 0, size, 0));
+        bound = true;
+        CUmemAccessDesc ad;
+        memset(&ad, 0, sizeof(ad));
+        ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = e->device; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        DRV(g_drv.MemAddressReserve(&uc, size, gran, 0, 0));
+        DRV(g_drv.MemMap(uc, size, 0, mem, 0));
+        uc_mapped = true;
+        DRV(g_drv.MemSetAccess(uc, size, &ad, 1));
+        DRV(g_drv.MemAddressReserve(&mcva, size, gran, 0, 0));
+        DRV(g_drv.MemMap(mcva, size, 0, mc, 0));
+        mc_mapped = true;
+        DRV(g_drv.MemSetAccess(mcva, size, &ad, 1));
+        // move the live state over (through the unicast mapping) and drop the cudaMalloc'ed tables
+        CU(cudaMemsetAsync((void*)uc, 0, size, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpyAsync((void*)uc, e->d_Xall, 2 * tbl, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaDeviceSynchronize());
+        return F2V_OK;
+    }();
+    if (rr != F2V_OK) {
+        close_all();
+        if (mc_mapped) g_drv.MemUnmap(mcva, size);
+        if (mcva) g_drv.MemAddressFree(mcva, size);
+        if (bound) g_drv.MulticastUnbind(mc, dev, 0, size);
+        if (uc_mapped) g_drv.MemUnmap(uc, size);
+        if (uc) g_drv.MemAddressFree(uc, size);
+        if (mem) g_drv.MemRelease(mem);
+        g_drv.MemRelease(mc);
+        return rr;
+    }
     CU(cudaFree(e->d_Xall));
     CU(cudaFree(e->d_flags));
     e->d_Xall = (float*)uc;
@@ -1396,7 +1537,7 @@ static int mc_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world) {
     e->d_flags = (uint64_t*)((char*)uc + flags_off);
     e->mc_handle = mc; e->vmm_handle = mem; e->vmm_uc = uc; e->vmm_mc = mcva; e->vmm_size = size;
     e->mc_mode = true;
-    if (handshake('C')) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: bind handshake failed"); }
+    if (handshake('C')) { close_all(); return fail(F2V_ERR_STATE, "multicast hand-off: bind handshake failed (a peer gave up?)"); }
     close_all();
     return F2V_OK;
 }
@@ -1451,6 +1592,7 @@ static int shard_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world
     if (rank == 0) {
         for (int k = 1; k < world; k++) {
             int c = accept(e->listen_sock, nullptr, nullptr);
+            if (c >= 0) sock_timeouts(c, kHandoffTimeoutS);
             char who = 0;
             if (c < 0 || recv(c, &who, 1, MSG_WAITALL) != 1 || who < 1 || who >= world || conns[(int)who] >= 0) {
                 if (c >= 0) close(c);
@@ -1469,6 +1611,7 @@ static int shard_setup(f2v_engine* e, const PeerBlob* blobs, int rank, int world
                     if (q != k && sock_send_fd(conns[k], fds[t][q]) != 0) { close_all(); return fail(F2V_ERR_STATE, "shard hand-off: send failed"); }
     } else {
         int c = socket(AF_UNIX, SOCK_STREAM, 0);
+        if (c >= 0) sock_timeouts(c, kHandoffTimeoutS);
         struct sockaddr_un a;
         socklen_t alen;
         sock_addr(&a, &alen, blobs[0].sock_name);

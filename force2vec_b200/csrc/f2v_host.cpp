@@ -13,7 +13,9 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <cerrno>
 #include <cmath>
+#include <sys/stat.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -125,7 +127,7 @@ inline void init_span(f2v_rng& g, float* X, uint64_t count) {
 }  // namespace
 
 extern "C" int f2v_init_embeddings(f2v_rng* g, int model, uint64_t n, uint32_t dim, float* X) {
-    if (!g || !X) return F2V_ERR_ARG;
+    if (!g || !X) return f2v::host_fail(F2V_ERR_ARG, "f2v_init_embeddings: bad argument or malformed input");
     const uint64_t total = n * (uint64_t)dim;
     constexpr uint64_t kChunk = 1ull << 20;
     const uint64_t nchunks = (total + kChunk - 1) / kChunk;
@@ -153,7 +155,7 @@ extern "C" int f2v_init_embeddings(f2v_rng* g, int model, uint64_t n, uint32_t d
 }
 
 extern "C" int f2v_build_lut(float* t) {
-    if (!t) return F2V_ERR_ARG;
+    if (!t) return f2v::host_fail(F2V_ERR_ARG, "f2v_build_lut: bad argument or malformed input");
     for (int i = 0; i < F2V_LUT_SIZE; i++) {
         // VALUETYPE x = 2.0*SM_BOUND*i/SM_TABLE_SIZE - SM_BOUND; 1.0/(1+exp(-x)) with the float exp
         float x = (float)(2.0 * 6.0 * i / F2V_LUT_SIZE - 6.0);
@@ -172,7 +174,7 @@ extern "C" uint64_t f2v_neg_stream_len(int model, uint64_t n, uint32_t batch, ui
 
 extern "C" int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint32_t batch, uint32_t s,
                                         int bs_mode, uint32_t* out) {
-    if (!g || !out || batch == 0 || n < 2) return F2V_ERR_ARG;
+    if (!g || !out || batch == 0 || n < 2) return f2v::host_fail(F2V_ERR_ARG, "f2v_draw_epoch_negatives: bad argument or malformed input");
     const uint64_t nb = (n + batch - 1) / batch;
     const bool window = bs_mode && model != F2V_WALK;
     const uint64_t W = window ? (uint64_t)batch + s - 1 : (uint64_t)s;
@@ -226,7 +228,7 @@ extern "C" int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint3
 
 extern "C" int f2v_draw_walks(f2v_rng* g, uint64_t n, uint64_t nnz, const uint64_t* rowptr,
                               const uint32_t* colids, uint32_t* walks) {
-    if (!g || !rowptr || !walks) return F2V_ERR_ARG;
+    if (!g || !rowptr || !walks) return f2v::host_fail(F2V_ERR_ARG, "f2v_draw_walks: bad argument or malformed input");
     for (uint64_t i = 0; i < n; i++) {
         uint64_t w = i;
         for (int l = 0; l < F2V_WALKLEN; l++) {
@@ -247,11 +249,11 @@ static int csr_from_pairs(uint64_t n, std::vector<uint32_t>& src, std::vector<ui
                           uint64_t* nnz_out, uint64_t** rowptr_out, uint32_t** colids_out) {
     const uint64_t m = src.size();
     uint64_t* rowptr = (uint64_t*)calloc(n + 1, sizeof(uint64_t));
-    if (!rowptr) return F2V_ERR_NOMEM;
+    if (!rowptr) return f2v::host_fail(F2V_ERR_NOMEM, "csr_from_pairs: out of host memory");
     for (uint64_t k = 0; k < m; k++) rowptr[src[k] + 1]++;
     for (uint64_t i = 0; i < n; i++) rowptr[i + 1] += rowptr[i];
     uint32_t* colids = (uint32_t*)malloc(sizeof(uint32_t) * (m ? m : 1));
-    if (!colids) { free(rowptr); return F2V_ERR_NOMEM; }
+    if (!colids) { free(rowptr); return f2v::host_fail(F2V_ERR_NOMEM, "csr_from_pairs: out of host memory"); }
     {
         std::vector<uint64_t> cur(rowptr, rowptr + n);
         for (uint64_t k = 0; k < m; k++) colids[cur[src[k]]++] = dst[k];
@@ -284,14 +286,16 @@ static int csr_from_pairs(uint64_t n, std::vector<uint32_t>& src, std::vector<ui
 
 extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint64_t** rowptr_out,
                             uint32_t** colids_out) {
-    if (!path || !n_out || !nnz_out || !rowptr_out || !colids_out) return F2V_ERR_ARG;
+    if (!path || !n_out || !nnz_out || !rowptr_out || !colids_out) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: bad argument or malformed input");
+    struct stat st;
+    if (stat(path, &st) != 0) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: cannot stat %s: %s", path, strerror(errno));
+    if (!S_ISREG(st.st_mode)) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: %s is not a regular file", path);
     FILE* f = fopen(path, "rb");
-    if (!f) return F2V_ERR_ARG;
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> buf((size_t)sz + 1);
-    if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return F2V_ERR_ARG; }
+    if (!f) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: cannot open %s: %s", path, strerror(errno));
+    const long sz = (long)st.st_size;
+    std::vector<char> buf;
+    try { buf.resize((size_t)sz + 1); } catch (const std::bad_alloc&) { fclose(f); return f2v::host_fail(F2V_ERR_NOMEM, "f2v_load_mtx: out of host memory (%ld-byte file)", sz); }
+    if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: short read on %s", path); }
     fclose(f);
     buf[sz] = 0;
     const char* p = buf.data();
@@ -317,10 +321,10 @@ extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out
         p = eol ? eol + 1 : end;
     };
     uint64_t m = 0, ncol = 0, cnt = 0;
-    if (!parse_u(m) || !parse_u(ncol) || !parse_u(cnt)) return F2V_ERR_ARG;
+    if (!parse_u(m) || !parse_u(ncol) || !parse_u(cnt)) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: %s: no \"rows cols entries\" size line", path);
     skip_line();
     const uint64_t n = std::max(m, ncol);
-    if (n < 1 || n > 0xffffffffull) return F2V_ERR_ARG;
+    if (n < 1 || n > 0xffffffffull) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: %s: matrix size %llu out of range", path, (unsigned long long)n);
     // The entry lines are parsed by all host threads: the data region is cut at line boundaries, every
     // piece yields its (row, col) pairs in file order, and the first `cnt` entries of the file are
     // kept (the size line decides how many there are, IO.h:95-106); which thread parsed an entry does
@@ -372,7 +376,7 @@ extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out
     }
     uint64_t have = 0;
     for (int t = 0; t < nt; t++) have += rows[t].size();
-    if (have < cnt) return F2V_ERR_ARG;                       // fewer entries than the size line says
+    if (have < cnt) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: %s: %llu entries, the size line says %llu", path, (unsigned long long)have, (unsigned long long)cnt);
     std::vector<uint32_t> src, dst;
     src.reserve(symmetric ? 2 * cnt : cnt);
     dst.reserve(symmetric ? 2 * cnt : cnt);
@@ -381,7 +385,7 @@ extern "C" int f2v_load_mtx(const char* path, uint64_t* n_out, uint64_t* nnz_out
         const uint64_t m_t = std::min<uint64_t>(rows[t].size(), cnt - taken);
         for (uint64_t k = 0; k < m_t; k++) {
             const uint32_t r = rows[t][k], c = cols[t][k];
-            if (r == 0xffffffffu) return F2V_ERR_ARG;          // malformed entry / index out of range
+            if (r == 0xffffffffu) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_mtx: %s: entry %llu is malformed or out of range", path, (unsigned long long)(taken + k + 1));
             if (symmetric) {
                 if (r == c) continue;                          // self-loops dropped (IO.h:130-134)
                 src.push_back(r); dst.push_back(c);
@@ -454,9 +458,9 @@ static int format_g6(char* out, float v) {
 extern "C" int f2v_format_g6(float v, char* out32) { int k = format_g6(out32, v); out32[k] = 0; return k; }
 
 extern "C" int f2v_write_embd(const char* path, const float* X, uint64_t n, uint32_t dim) {
-    if (!path || !X) return F2V_ERR_ARG;
+    if (!path || !X) return f2v::host_fail(F2V_ERR_ARG, "f2v_write_embd: bad argument or malformed input");
     FILE* f = fopen(path, "wb");
-    if (!f) return F2V_ERR_ARG;
+    if (!f) return f2v::host_fail(F2V_ERR_ARG, "f2v_write_embd: bad argument or malformed input");
     fprintf(f, "%llu %u\n", (unsigned long long)n, dim);
     // rows are formatted in parallel blocks, written in order; "%.6g" is what ostream << float emits
     const uint64_t block = 4096;
@@ -497,9 +501,9 @@ extern "C" int f2v_write_embd(const char* path, const float* X, uint64_t n, uint
 // Binary CSR cache: "F2VCSR01", u64 n, u64 nnz, rowptr u64[n+1], colids u32[nnz].  The text loader
 // parses ~10 M entries/s; a scale-24 graph (0.5 G entries) is minutes as text and seconds like this.
 extern "C" int f2v_write_csr(const char* path, uint64_t n, uint64_t nnz, const uint64_t* rowptr, const uint32_t* colids) {
-    if (!path || !rowptr || (nnz && !colids) || rowptr[n] != nnz) return F2V_ERR_ARG;
+    if (!path || !rowptr || (nnz && !colids) || rowptr[n] != nnz) return f2v::host_fail(F2V_ERR_ARG, "f2v_write_csr: bad argument or malformed input");
     FILE* f = fopen(path, "wb");
-    if (!f) return F2V_ERR_ARG;
+    if (!f) return f2v::host_fail(F2V_ERR_ARG, "f2v_write_csr: bad argument or malformed input");
     const char magic[8] = {'F', '2', 'V', 'C', 'S', 'R', '0', '1'};
     bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&nnz, 8, 1, f) == 1 &&
               fwrite(rowptr, 8, n + 1, f) == n + 1 && (nnz == 0 || fwrite(colids, 4, nnz, f) == nnz);
@@ -508,13 +512,13 @@ extern "C" int f2v_write_csr(const char* path, uint64_t n, uint64_t nnz, const u
 }
 
 extern "C" int f2v_load_csr(const char* path, uint64_t* n_out, uint64_t* nnz_out, uint64_t** rowptr_out, uint32_t** colids_out) {
-    if (!path || !n_out || !nnz_out || !rowptr_out || !colids_out) return F2V_ERR_ARG;
+    if (!path || !n_out || !nnz_out || !rowptr_out || !colids_out) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_csr: bad argument or malformed input");
     FILE* f = fopen(path, "rb");
-    if (!f) return F2V_ERR_ARG;
+    if (!f) return f2v::host_fail(F2V_ERR_ARG, "f2v_load_csr: bad argument or malformed input");
     char magic[8];
     uint64_t n = 0, nnz = 0;
     if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "F2VCSR01", 8) != 0 || fread(&n, 8, 1, f) != 1 ||
-        fread(&nnz, 8, 1, f) != 1 || n < 1 || n > 0xffffffffull) { fclose(f); return F2V_ERR_ARG; }
+        fread(&nnz, 8, 1, f) != 1 || n < 1 || n > 0xffffffffull) { fclose(f); return f2v::host_fail(F2V_ERR_ARG, "f2v_load_csr: bad argument or malformed input"); }
     uint64_t* rp = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
     uint32_t* ci = (uint32_t*)malloc(sizeof(uint32_t) * (nnz ? nnz : 1));
     bool ok = rp && ci && fread(rp, 8, n + 1, f) == n + 1 && (nnz == 0 || fread(ci, 4, nnz, f) == nnz);
@@ -528,9 +532,9 @@ extern "C" int f2v_load_csr(const char* path, uint64_t* n_out, uint64_t* nnz_out
 }
 
 extern "C" int f2v_write_mtx(const char* path, uint64_t n, const uint64_t* rowptr, const uint32_t* colids) {
-    if (!path || !rowptr) return F2V_ERR_ARG;
+    if (!path || !rowptr) return f2v::host_fail(F2V_ERR_ARG, "f2v_write_mtx: bad argument or malformed input");
     FILE* f = fopen(path, "wb");
-    if (!f) return F2V_ERR_ARG;
+    if (!f) return f2v::host_fail(F2V_ERR_ARG, "f2v_write_mtx: bad argument or malformed input");
     uint64_t cnt = 0;
     for (uint64_t i = 0; i < n; i++)
         for (uint64_t e = rowptr[i]; e < rowptr[i + 1]; e++)
@@ -586,7 +590,7 @@ static inline void rmat_edge(int scale, uint64_t seed, uint64_t k, uint32_t& u, 
 extern "C" int f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t* n_out, uint64_t* nnz_out,
                             uint64_t** rowptr_out, uint32_t** colids_out) {
     if (scale < 2 || scale > 31 || edge_factor < 1 || !n_out || !nnz_out || !rowptr_out || !colids_out)
-        return F2V_ERR_ARG;
+        return f2v::host_fail(F2V_ERR_ARG, "f2v_rmat_csr: bad argument or malformed input");
     const uint64_t n = 1ull << scale, m = (uint64_t)edge_factor * n;
     std::vector<uint32_t> degc(n, 0);
 #pragma omp parallel for schedule(static)
@@ -598,12 +602,12 @@ extern "C" int f2v_rmat_csr(int scale, int edge_factor, uint64_t seed, uint64_t*
         __atomic_fetch_add(&degc[v], 1u, __ATOMIC_RELAXED);
     }
     uint64_t* rowptr = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
-    if (!rowptr) return F2V_ERR_NOMEM;
+    if (!rowptr) return f2v::host_fail(F2V_ERR_NOMEM, "f2v_rmat_csr: out of host memory");
     rowptr[0] = 0;
     for (uint64_t i = 0; i < n; i++) rowptr[i + 1] = rowptr[i] + degc[i];
     const uint64_t tot = rowptr[n];
     uint32_t* colids = (uint32_t*)malloc(sizeof(uint32_t) * (tot ? tot : 1));
-    if (!colids) { free(rowptr); return F2V_ERR_NOMEM; }
+    if (!colids) { free(rowptr); return f2v::host_fail(F2V_ERR_NOMEM, "f2v_rmat_csr: out of host memory"); }
     std::vector<uint64_t> cur(rowptr, rowptr + n);
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < (int64_t)m; k++) {
@@ -643,7 +647,7 @@ extern "C" int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64
                               uint64_t** item_ptr, uint32_t** n_hub, void** items, void** hub) {
     if (!rowptr || !nb || !item_ptr || !n_hub || !items || !hub || batch == 0 || world < 1 || rank < 0 ||
         rank >= world || chunk == 0 || assign < 0 || assign > 7)
-        return F2V_ERR_ARG;
+        return f2v::host_fail(F2V_ERR_ARG, "f2v_plan_build: bad argument or malformed input");
     f2v::HostPlan hp;
     f2v::build_host_plan(rowptr, first_row, nrows, batch, chunk, par, walk != 0, rank, world, assign, hp);
     const size_t total = hp.item_ptr[hp.nb];
@@ -652,7 +656,7 @@ extern "C" int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64
     *n_hub = (uint32_t*)malloc(sizeof(uint32_t) * (hp.nb ? hp.nb : 1));
     *items = malloc(sizeof(f2v::Item) * (total ? total : 1));
     *hub = malloc(sizeof(f2v::HubInfo) * (total ? total : 1));
-    if (!*item_ptr || !*n_hub || !*items || !*hub) return F2V_ERR_NOMEM;
+    if (!*item_ptr || !*n_hub || !*items || !*hub) return f2v::host_fail(F2V_ERR_NOMEM, "f2v_plan_build: out of host memory");
     memcpy(*item_ptr, hp.item_ptr.data(), sizeof(uint64_t) * (hp.nb + 1));
     if (hp.nb) memcpy(*n_hub, hp.n_hub.data(), sizeof(uint32_t) * hp.nb);
     if (total) {
@@ -664,8 +668,8 @@ extern "C" int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64
 
 // ------------------------------------------------------------------ driver -------------
 extern "C" int f2v_train(const f2v_train_args* a, float* X_out, double* seconds) {
-    if (!a || !X_out || !a->rowptr) return F2V_ERR_ARG;
-    if (a->option != F2V_TDIST && a->option != F2V_SIGMOID && a->option != F2V_WALK) return F2V_ERR_ARG;
+    if (!a || !X_out || !a->rowptr) return f2v::host_fail(F2V_ERR_ARG, "f2v_train: bad argument or malformed input");
+    if (a->option != F2V_TDIST && a->option != F2V_SIGMOID && a->option != F2V_WALK) return f2v::host_fail(F2V_ERR_ARG, "f2v_train: bad argument or malformed input");
     const int model = a->option;
     const int bs = model == F2V_WALK ? 0 : (a->bs ? 1 : 0);   // -bs ignored by option 7
     f2v_engine* e = nullptr;
@@ -676,7 +680,7 @@ extern "C" int f2v_train(const f2v_train_args* a, float* X_out, double* seconds)
     if (a->epoch_mode) { rc = f2v_set_epoch_mode(e, a->epoch_mode); if (rc) return rc; }
     auto t0 = std::chrono::steady_clock::now();      // algorithms.cpp:557 -- the timer starts before init
     f2v_rng* g = gd.g = f2v_rng_create(a->seed);
-    if (!g) return F2V_ERR_NOMEM;
+    if (!g) return f2v::host_fail(F2V_ERR_NOMEM, "f2v_train: out of host memory");
     f2v_init_embeddings(g, model, a->n, a->dim, X_out);
     rc = f2v_set_embeddings(e, X_out);
     if (rc) return rc;
@@ -734,31 +738,46 @@ extern "C" int f2v_train(const f2v_train_args* a, float* X_out, double* seconds)
 // walks / negatives of every epoch into host buffers all threads upload from, so the result is the
 // single-GPU result bit for bit (for equal `chunk`).
 namespace {
-struct SpinBarrier {
+// Barrier whose wait() also tells every thread, identically, whether any thread had failed when the
+// LAST one arrived.  Threads branch only on that value, so they all run the same number of barriers
+// (a thread that read a shared flag on its own could leave the loop one barrier earlier than a peer
+// and pair its post-loop wait with the peer's in-loop wait: a hang instead of an error).
+struct FailBarrier {
     std::mutex m;
     std::condition_variable cv;
     int count = 0, gen = 0, parties;
-    explicit SpinBarrier(int n) : parties(n) {}
-    void wait() {
+    bool stop[2] = {false, false};       // decision of generation g lives in stop[g & 1]
+    std::atomic<int>& failed;
+    FailBarrier(int n, std::atomic<int>& f) : parties(n), failed(f) {}
+    bool wait() {                        // true = somebody failed: stop together
         std::unique_lock<std::mutex> lk(m);
         const int g = gen;
-        if (++count == parties) { count = 0; gen++; cv.notify_all(); }
+        if (++count == parties) { stop[g & 1] = failed.load() != 0; count = 0; gen++; cv.notify_all(); }
         else cv.wait(lk, [&] { return gen != g; });
+        return stop[g & 1];
     }
 };
 }  // namespace
 
+// test hook: make the given rank fail at the given epoch's upload (F2V_TEST_FAIL_RANK / F2V_TEST_FAIL_EPOCH)
+static int injected_failure(int rank, uint32_t epoch) {
+    const char* fr = getenv("F2V_TEST_FAIL_RANK");
+    if (!fr || atoi(fr) != rank) return F2V_OK;
+    const char* fe = getenv("F2V_TEST_FAIL_EPOCH");
+    return (fe ? (uint32_t)atoi(fe) : 0u) == epoch ? F2V_ERR_STATE : F2V_OK;
+}
+
 extern "C" int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, double* seconds) {
     if (gpus <= 1) return f2v_train(a, X_out, seconds);
-    if (!a || !X_out || !a->rowptr) return F2V_ERR_ARG;
-    if (a->option != F2V_TDIST && a->option != F2V_SIGMOID && a->option != F2V_WALK) return F2V_ERR_ARG;
-    if (gpus > 8 || gpus > f2v_device_count()) return F2V_ERR_ARG;
+    if (!a || !X_out || !a->rowptr) return f2v::host_fail(F2V_ERR_ARG, "f2v_train_gpus: bad argument or malformed input");
+    if (a->option != F2V_TDIST && a->option != F2V_SIGMOID && a->option != F2V_WALK) return f2v::host_fail(F2V_ERR_ARG, "f2v_train_gpus: bad argument or malformed input");
+    if (gpus > 8 || gpus > f2v_device_count()) return f2v::host_fail(F2V_ERR_ARG, "f2v_train_gpus: bad argument or malformed input");
     const int model = a->option;
     const int bs = model == F2V_WALK ? 0 : (a->bs ? 1 : 0);
     const int G = gpus;
     auto t0 = std::chrono::steady_clock::now();
     f2v_rng* g = f2v_rng_create(a->seed);
-    if (!g) return F2V_ERR_NOMEM;
+    if (!g) return f2v::host_fail(F2V_ERR_NOMEM, "f2v_train_gpus: out of host memory");
     f2v_init_embeddings(g, model, a->n, a->dim, X_out);
     float lut[F2V_LUT_SIZE];
     f2v_build_lut(lut);
@@ -769,42 +788,45 @@ extern "C" int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, d
     std::vector<char> blobs((size_t)G * F2V_PEER_BLOB);
     std::vector<int> status(G, F2V_OK);
     std::vector<std::string> errs(G);
-    SpinBarrier bar(G);
     std::atomic<int> failed{0};
+    FailBarrier bar(G, failed);
     auto worker = [&](int r) {
         f2v_engine* e = nullptr;
         int rc = F2V_OK;
-        auto step = [&](int code) {          // record the first error of this thread; all threads meet at the
-            if (code && !rc) { rc = code; errs[r] = f2v_last_error(); failed.store(1); }   // next barrier and stop together
+        auto step = [&](int code) {          // record the first error of this thread; every thread learns of it
+            if (code && !rc) { rc = code; errs[r] = f2v_last_error(); failed.store(1); }   // at the next barrier
         };
         step(f2v_create(&e, a->device + r, a->n, a->nnz, a->rowptr, a->colids, a->dim));
         if (!rc && a->epoch_mode) step(f2v_set_epoch_mode(e, a->epoch_mode));
         if (!rc) step(f2v_comm_peer_export(e, blobs.data() + (size_t)r * F2V_PEER_BLOB));
-        bar.wait();
-        if (!failed.load()) step(f2v_comm_peer_init(e, blobs.data(), r, G));
-        bar.wait();
-        if (!failed.load()) {
+        bool stop = bar.wait();
+        if (!stop) step(f2v_comm_peer_init(e, blobs.data(), r, G));
+        stop = bar.wait();
+        if (!stop) {
             if (model != F2V_TDIST) step(f2v_set_lut(e, lut, F2V_LUT_SIZE));
             step(f2v_set_embeddings(e, X_out));
         }
-        bar.wait();
-        for (uint32_t it = 0; it < a->iterations && !failed.load(); it++) {
+        stop = bar.wait();
+        // every thread takes the same decisions (the barrier's return value), so every thread runs
+        // the same number of barriers whatever fails where
+        for (uint32_t it = 0; it < a->iterations && !stop; it++) {
             if (r == 0) {                    // the serial draws of this epoch (reference order: walks, then negatives)
                 if (host_walks) step(f2v_draw_walks(g, a->n, a->nnz, a->rowptr, a->colids, walks.data()));
                 step(f2v_draw_epoch_negatives(g, model, a->n, a->batch, a->nsamples, bs, neg.data()));
             }
-            bar.wait();
-            if (failed.load()) break;
-            if (model == F2V_WALK) step(host_walks ? f2v_set_walks(e, walks.data()) : f2v_sample_walks(e, a->seed, it));
-            step(f2v_set_negatives(e, neg.data(), slen));
+            stop = bar.wait();
+            if (stop) break;
+            if (injected_failure(r, it)) step(f2v::host_fail(F2V_ERR_STATE, "injected failure on rank %d, epoch %u (test hook)", r, it));
+            if (!rc && model == F2V_WALK) step(host_walks ? f2v_set_walks(e, walks.data()) : f2v_sample_walks(e, a->seed, it));
+            if (!rc) step(f2v_set_negatives(e, neg.data(), slen));
             if (!rc) step(f2v_sync(e));      // the host buffers are redrawn by thread 0 after the next barrier
-            bar.wait();
-            if (failed.load()) break;        // nobody has launched this epoch yet: safe to stop together
+            stop = bar.wait();
+            if (stop) break;                 // nobody has launched this epoch yet: safe to stop together
             step(f2v_run_epoch(e, model, a->batch, a->nsamples, bs, a->lr, a->chunk));
         }
         if (e && !rc) step(f2v_sync(e));
-        bar.wait();
-        if (r == 0 && !failed.load()) step(f2v_get_embeddings(e, X_out));
+        stop = bar.wait();
+        if (r == 0 && !stop) step(f2v_get_embeddings(e, X_out));
         bar.wait();                          // nobody unmaps a table a peer may still be storing into
         if (e) f2v_destroy(e);
         status[r] = rc;

@@ -10,6 +10,9 @@
 
 namespace f2v {
 
+// Sets the calling thread's f2v_last_error() message and returns `code` (defined in f2v_engine.cu).
+int host_fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+
 // CSR as the reference's CSR<INDEXTYPE,VALUETYPE> (sample/CSR.h:89-96) holds it, minus the
 // unused `values`; rowptr widened to 64 bit (the reference wraps at 2^32).
 struct Csr {

@@ -85,6 +85,10 @@ struct BatchParams {
     const uint64_t* flags;               // local flag page: flags[r * kFlagStride] written by rank r
     uint64_t wait_step;                  // before reading the next table: every peer's flag >= wait_step (0 = no wait)
     uint64_t signal_step;                // after the last CTA's stores: peers' flags := signal_step
+    uint64_t publish_step;               // != 0: CTA 0 publishes this step once the PREDECESSOR launch is complete
+                                         // (stream order / griddepcontrol.wait): the kernel boundary has flushed the
+                                         // predecessor's peer stores, so no system-scope fence per CTA and no extra
+                                         // launch is needed to hand minibatch b-1's rows to the peers
     uint32_t* done;                      // CTA arrival counter of the launch
     uint32_t n_store;                    // peers that receive unicast row stores (0 with multicast, or in timing probes)
     // NVLink multicast (NVLS): `mc_out` is the multicast mapping of the `out` table -- ONE store
@@ -102,6 +106,8 @@ struct BatchParams {
     // griddepcontrol.wait.  pdl = 2: the item's own row (from the current table, last written one
     // epoch ago) is also fetched before the wait.
     int pdl;
+    int late_wait;        // multi-GPU: 1 = every warp waits for the peers' flags after its dependency wait
+                          // (PDL-chained launches); 0 = one CTA-wide wait at kernel entry
 };
 
 // What changes from one minibatch to the next (the rest of BatchParams is constant over an epoch).
@@ -170,6 +176,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS.E.BYPASS.128), bypassing L1; src_bytes = 0
+// reads nothing and fills the destination with zeros.  Completion: cp.async.wait_group.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 // Programmatic dependent launch (sm_90+): wait for the prerequisite grid's completion and memory
 // flush / allow the dependent grid to be scheduled.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -236,6 +255,7 @@ struct VecL {
     static constexpr int NE = 4 * VPL;
     static constexpr int U = U_;
     static constexpr bool kBulk = true;
+    static constexpr int kStages = 0;        // > 0: RingL (asynchronous shared-memory ring, gather_stream)
     static_assert(V4 % LPR == 0 && VPL >= 1 && U <= LPR && LPR % U == 0, "bad layout");
     __device__ static __forceinline__ size_t stride(uint32_t) { return D; }
     __device__ static __forceinline__ void load_g(float (&f)[NE], const float* row, int l, uint32_t) {
@@ -316,6 +336,22 @@ struct VecL {
     }
 };
 
+// RingL<D,LPR,S,MINB>: the VecL<D,LPR,2> fragment layout, but gathered rows do not land in registers:
+// every lane group owns a ring of S stages x 2 rows in shared memory that it fills with 16-byte
+// asynchronous copies (cp.async.cg -> SASS LDGSTS, L2 -> shared memory, no register, no L1
+// allocation) S-1 stages ahead of the stage it computes on.  Bytes in flight per SM are then bounded
+// by shared memory (up to ~190 KB) instead of by landing registers (~64 KB at full occupancy,
+// and none while a warp computes), which is what the latency-bound gather needs.
+// A lane reads back exactly the 16-byte pieces it copied itself, so cp.async.wait_group is the
+// only synchronisation: no barrier, no cross-lane visibility.
+template <int D, int LPR_, int S_, int MINB_>
+struct RingL : VecL<D, LPR_, 2, MINB_> {
+    static constexpr int kStages = S_;
+    static constexpr uint32_t kRowBytes = D * 4;
+    static constexpr uint32_t kGroupBytes = S_ * 2 * kRowBytes;                 // ring of one lane group
+    static constexpr uint32_t kCtaBytes = kWarpsPerCta * (32 / LPR_) * kGroupBytes;
+};
+
 // GenL<NV>: any dim <= 32*NV; one group per warp, lane l holds elements l, l+32, ... (scalar
 // loads, still coalesced).
 template <int NV>
@@ -326,6 +362,7 @@ struct GenL {
     static constexpr int NE = NV;
     static constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
     static constexpr bool kBulk = false;
+    static constexpr int kStages = 0;
     __device__ static __forceinline__ size_t stride(uint32_t dim) { return dim; }
     __device__ static __forceinline__ void load_g(float (&f)[NE], const float* row, int l, uint32_t dim) {
 #pragma unroll
@@ -523,6 +560,127 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
     }
 }
 
+
+// Per-pair scalar / update with the pair's class (attractive or repulsive) known only at run time:
+// the unified row stream of gather_stream() mixes an item's neighbours and its per-vertex negatives,
+// and the lane groups of a warp sit at different positions of their streams.  Arithmetic identical
+// to the templated versions above, operation for operation.
+template <int MODEL, bool LS>
+__device__ __forceinline__ float pair_scalar_rt(float r, bool attr, float lr, float sd, const float* __restrict__ lut) {
+    if (MODEL == kTDist) {
+        const float one_r = __fadd_rn(1.0f, r);
+        return __fdiv_rn(attr ? -2.0f : 2.0f, attr ? one_r : __fmul_rn(r, one_r));
+    }
+    const float sg = fast_sm<LS>(lut, r);
+    return attr ? fmaf(-sd, sg, sd) : __fmul_rn(lr, sg);
+}
+template <class L, int MODEL>
+__device__ __forceinline__ void pair_apply_rt(float (&acc)[L::NE], const float (&xp)[L::NE], const float (&d)[L::NE],
+                                              float sc, bool valid, bool attr, float lr) {
+    if (MODEL == kTDist) L::clamp_acc(acc, d, sc, valid ? lr : 0.f);
+    else if (attr) L::axpy(acc, valid ? sc : 0.f, xp);
+    else L::sub_mul(acc, valid ? sc : 0.f, xp);
+}
+template <class L, int MODEL, bool LS>
+__device__ __forceinline__ void pair2_update_rt(float (&acc)[L::NE], const float (&xi)[L::NE],
+                                                const float (&x0)[L::NE], const float (&x1)[L::NE],
+                                                bool v0, bool v1, bool a0, bool a1, float lr, float sd,
+                                                const float* __restrict__ lut, int l) {
+    constexpr int H = L::LPR / 2;
+    float d0[L::NE], d1[L::NE];
+    const float p0 = MODEL == kTDist ? L::diff_ss(d0, xi, x0) : L::dot(xi, x0);
+    const float p1 = MODEL == kTDist ? L::diff_ss(d1, xi, x1) : L::dot(xi, x1);
+    const bool hi = (l & H) != 0;
+    float keep = hi ? p1 : p0;
+    keep += __shfl_xor_sync(kFull, hi ? p0 : p1, H);
+#pragma unroll
+    for (int off = H / 2; off >= 1; off >>= 1) keep += __shfl_xor_sync(kFull, keep, off);
+    const float mine = pair_scalar_rt<MODEL, LS>(keep, hi ? a1 : a0, lr, sd, lut);
+    const float other = __shfl_xor_sync(kFull, mine, H);
+    const float s0 = hi ? other : mine, s1 = hi ? mine : other;
+    pair_apply_rt<L, MODEL>(acc, x0, d0, s0, v0, a0, lr);
+    pair_apply_rt<L, MODEL>(acc, x1, d1, s1, v1, a1, lr);
+}
+
+// The asynchronous gather (RingL layouts).  An item's rows form ONE stream: its cntA attractive rows
+// (CSR neighbours / walk samples, ids at idxA) followed by its cntB repulsive rows (per-vertex
+// negatives, ids at idxB) -- the reference's order (algorithms.cpp:598-627).  The group copies the
+// stream two rows (one stage) at a time into its shared-memory ring, S-1 stages ahead of the stage it
+// computes on, so the copies of the next rows are in flight WHILE the current pair is reduced and
+// applied, and a short row's negatives are already on their way while its neighbours are processed.
+// Ids are fetched LPR at a time (one coalesced load per group), one block ahead of the copy pointer.
+// All groups of the warp run the same number of stages (the reductions are warp-wide); slots past a
+// group's own stream are zero-filled without touching memory and contribute exactly zero.
+template <class L, int MODEL, bool LS>
+__device__ __forceinline__ void gather_stream(float (&acc)[L::NE], const float (&xi)[L::NE],
+                                              const uint32_t* __restrict__ idxA, uint32_t cntA,
+                                              const uint32_t* __restrict__ idxB, uint32_t cntB,
+                                              uint32_t self, const BatchParams& p, uint32_t split, float sd, int l,
+                                              const float* __restrict__ lut, uint32_t ring, bool have_first,
+                                              uint32_t first) {
+    constexpr int LPR = L::LPR, S = L::kStages, VPL = L::VPL;
+    constexpr uint32_t RB = L::kRowBytes;
+    static_assert(S >= 2 && LPR % 2 == 0, "ring layout");
+    const uint32_t cnt = cntA + cntB;
+    const uint32_t cnt_max = L::G > 1 ? warp_max(cnt) : cnt;
+    if (cnt_max == 0) return;
+    const uint32_t nst = (cnt_max + 1) >> 1;
+    const float* const Xb = p.Xb;
+    // this lane's id (as a row of the combined table) at stream position base + l
+    auto load_ids = [&](uint32_t base) -> uint32_t {
+        const uint32_t P = base + (uint32_t)l;
+        uint32_t j = self;
+        if (P < cntA) j = __ldcg(idxA + P);
+        else if (P < cnt) j = __ldcg(idxB + (P - cntA));
+        return table_row(p, j, split);
+    };
+    uint32_t ids_cur = have_first ? table_row(p, first, split) : load_ids(0);   // block of the copy pointer
+    uint32_t ids_nxt = cnt_max > (uint32_t)LPR ? load_ids(LPR) : 0u;             // the block after it
+    uint32_t blk = 0;                                                            // block index of ids_cur
+    const uint32_t lane_off = (uint32_t)l * 16u;
+    auto issue = [&](uint32_t st) {
+        const uint32_t q0 = 2u * st;
+        if (q0 / LPR != blk) {                       // the copy pointer enters the next id block (warp-uniform)
+            blk++;
+            ids_cur = ids_nxt;
+            ids_nxt = cnt_max > (blk + 1) * LPR ? load_ids((blk + 1) * LPR) : 0u;
+        }
+        const uint32_t slot = ring + (st % S) * 2u * RB + lane_off;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t q = q0 + u;
+            const uint32_t j = __shfl_sync(kFull, ids_cur, q % LPR, LPR);
+            const uint32_t nbytes = q < cnt ? 16u : 0u;                        // past the stream: zero fill, no read
+            const float* src = Xb + (size_t)j * (RB / 4) + (uint32_t)l * 4u;
+#pragma unroll
+            for (int k = 0; k < VPL; k++)
+                cp_async16(slot + u * RB + k * LPR * 16u, src + k * LPR * 4, nbytes);
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < S - 1; st++) {
+        if ((uint32_t)st < nst) issue(st);
+        cp_async_commit();
+    }
+    for (uint32_t k = 0; k < nst; k++) {
+        if (k + S - 1 < nst) issue(k + S - 1);
+        cp_async_commit();                           // one group per iteration (possibly empty): uniform accounting
+        cp_async_wait<S - 1>();                      // stage k has landed (this lane's own pieces)
+        const uint32_t slot = ring + (k % S) * 2u * RB + lane_off;
+        float x0[L::NE], x1[L::NE];
+#pragma unroll
+        for (int c = 0; c < VPL; c++) {
+            const float4 a = lds128(slot + c * LPR * 16u);
+            const float4 b = lds128(slot + RB + c * LPR * 16u);
+            x0[4 * c + 0] = a.x; x0[4 * c + 1] = a.y; x0[4 * c + 2] = a.z; x0[4 * c + 3] = a.w;
+            x1[4 * c + 0] = b.x; x1[4 * c + 1] = b.y; x1[4 * c + 2] = b.z; x1[4 * c + 3] = b.w;
+        }
+        const uint32_t q0 = 2u * k;
+        pair2_update_rt<L, MODEL, LS>(acc, xi, x0, x1, q0 < cnt, q0 + 1 < cnt, q0 < cntA, q0 + 1 < cntA, p.lr, sd, lut, l);
+    }
+    cp_async_wait<0>();
+}
+
 // acc = rows[0] + rows[1] + ... + rows[cnt-1] (in that order), CU partial rows in flight.
 template <class L>
 __device__ __forceinline__ void fold_rows(float (&acc)[L::NE], const float* rows, uint32_t cnt, size_t rs,
@@ -548,13 +706,34 @@ __device__ __forceinline__ void fold_rows(float (&acc)[L::NE], const float* rows
     }
 }
 
+__device__ __forceinline__ void publish_step(const BatchParams& p, uint64_t step) {
+    if (p.mc_flag != nullptr) { mc_st_release_sys(p.mc_flag, step); return; }
+    for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], step);
+}
+
+// The same wait done by one warp on its own (lanes 0..world-1 poll one flag each): used after the
+// warp's griddepcontrol.wait, where a CTA-wide barrier would serialise the warps' prologues.
+__device__ __forceinline__ void peer_wait_warp(const BatchParams& p, int lane) {
+    if (p.wait_step == 0) return;
+    if ((uint32_t)lane < p.world && ((uint32_t)lane != p.rank || p.mc_flag != nullptr))
+        wait_flag(p.flags + (size_t)lane * kFlagStride, p.wait_step, p.timeout_ns, p.timed_out);
+    __syncwarp();
+}
+
+// Predecessor complete (the caller has passed griddepcontrol.wait, or the launch is an ordinary
+// stream-ordered one): its rows are performed in every replica, so its step can be published.
+__device__ __forceinline__ void publish_predecessor(const BatchParams& p) {
+    if (p.publish_step != 0 && p.n_peers != 0 && blockIdx.x == 0 && threadIdx.x == 0) publish_step(p, p.publish_step);
+}
+
 // G work items, one per group: items t_base .. t_base+G-1 (groups past n_items idle).
 // s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
 template <class L, int MODEL, bool LS>
 __device__ __forceinline__ void process_items(const BatchParams& p, const BatchVar& bv, uint32_t t_base,
                                               const float* s_neg, uint64_t* neg_bar, uint32_t neg_parity, int lane,
-                                              const float* __restrict__ lut) {
+                                              const float* __restrict__ lut, uint32_t ring_base = 0) {
     constexpr int NE = L::NE, LPR = L::LPR;
+    constexpr bool kRing = L::kStages > 0;
     const int g = lane / LPR, l = lane % LPR;
     const size_t rs = L::stride(p.dim);
     const uint32_t t = t_base + g;
@@ -573,6 +752,12 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     const bool early_idx = p.pdl != 0 && MODEL != kWalk;     // walks may have been sampled by the predecessor kernel
     uint32_t first = v;
     if (early_idx && (uint32_t)l < min((uint32_t)LPR, nbr_cnt)) first = __ldg(nbr + l);
+    // asynchronous-ring layouts: a row's per-vertex negatives (bs=1, or shared negatives that are not
+    // staged in shared memory) ride in the same stream as its neighbours; hub chunks take theirs after
+    // the fold.  The negative stream is uploaded before the epoch's first (ordinary) launch: static here.
+    const uint32_t* const nidx = bv.neg + ((p.bs_mode && active) ? (size_t)(v - bv.lo) : 0);
+    const uint32_t negB = (kRing && s_neg == nullptr && active && !is_chunk) ? p.s : 0u;
+    if (kRing && early_idx && (uint32_t)l >= nbr_cnt && (uint32_t)l < nbr_cnt + negB) first = __ldcg(nidx + ((uint32_t)l - nbr_cnt));
     float xi[NE];
     if (p.pdl == 1) { pdl_wait(); pdl_launch_dependents(); }
     if (active) L::load_g(xi, p.Xb + (size_t)table_row(p, v, bv.split) * rs, l, p.dim);
@@ -583,6 +768,9 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     // the dependent launch is released only after this one's own wait: when minibatch b+1 starts,
     // minibatch b-1 is therefore complete
     if (p.pdl == 2) { pdl_wait(); pdl_launch_dependents(); }
+    // multi-GPU: rows of the next table written by the peers' previous minibatch (the item's own row
+    // comes from the current table, which nobody writes during this epoch)
+    if (p.late_wait) peer_wait_warp(p, lane);
     float sd = 0.f;
     if (MODEL != kTDist) {
         // degi = 1.0/(deg+1) stored to float (algorithms.cpp:852,1159); STEP*degi in float
@@ -595,7 +783,13 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
 #pragma unroll
     for (int k = 0; k < NE; k++) acc[k] = start_at_xi ? xi[k] : 0.f;
 
-    gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, early_idx, first);
+    uint32_t ring = 0;
+    if constexpr (kRing) {
+        ring = ring_base + (uint32_t)(((threadIdx.x >> 5) * L::G + g) * L::kGroupBytes);
+        gather_stream<L, MODEL, LS>(acc, xi, nbr, nbr_cnt, nidx, negB, v, p, bv.split, sd, l, lut, ring, early_idx, first);
+    } else {
+        gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, early_idx, first);
+    }
 
     // split rows: publish this chunk's partial sum; the last chunk of a fold block (kFoldBlock
     // consecutive chunks) to arrive folds the block in chunk order and -- rows with more than one
@@ -603,7 +797,8 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     // order and finishes the row.  Deterministic (no float atomics), and the fold's critical path
     // is ~kFoldBlock + nchunks/kFoldBlock partial rows instead of nchunks.
     bool finish = active;
-    if (__any_sync(kFull, is_chunk)) {
+    const bool any_chunk = __any_sync(kFull, is_chunk);
+    if (any_chunk) {
         const uint32_t slot0 = h.slot - h.chunk;
         const uint32_t nblk = (h.nchunks + kFoldBlock - 1) / kFoldBlock;
         const uint32_t blk = h.chunk / kFoldBlock;
@@ -654,8 +849,13 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
             L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
             pair_update<L, MODEL, false, LS>(acc, xi, row, finish, p.lr, sd, lut);
         }
+    } else if constexpr (kRing) {
+        // rows that were not split took their negatives in the stream above; a split row's negatives
+        // follow the fold (the chunk that finished the row)
+        if (any_chunk)
+            gather_stream<L, MODEL, LS>(acc, xi, nbr, 0u, nidx, (is_chunk && finish) ? p.s : 0u, v, p, bv.split, sd, l, lut,
+                                        ring, false, 0u);
     } else {
-        const uint32_t* nidx = bv.neg + ((p.bs_mode && active) ? (size_t)(v - bv.lo) : 0);
         gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, bv.split, sd, l, lut);
     }
     if (finish) {
@@ -686,11 +886,6 @@ __device__ __forceinline__ void peer_wait(const BatchParams& p) {
         wait_flag(f, p.wait_step, p.timeout_ns, p.timed_out);
     }
     __syncthreads();
-}
-
-__device__ __forceinline__ void publish_step(const BatchParams& p, uint64_t step) {
-    if (p.mc_flag != nullptr) { mc_st_release_sys(p.mc_flag, step); return; }
-    for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], step);
 }
 
 // Exchange barrier, exit side: the last CTA of the launch to finish its (local and peer) stores
@@ -740,15 +935,16 @@ force_batch_kernel(const BatchParams p) {
     const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
     const float* lut = p.lut;
     const BatchVar bv = batch_var(p);
-    peer_wait(p);
+    if (!p.late_wait) { publish_predecessor(p); peer_wait(p); }
     if (negs || LS) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
         if (threadIdx.x < 32) {
             const uint32_t lut_bytes = LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u;
             if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes + lut_bytes);
-            if (p.wait_step) fence_proxy_async();   // rows written by peers (generic proxy) are read by TMA next
-            if (p.pdl) { pdl_wait(); fence_proxy_async(); }   // negative rows may have been written by the previous minibatch
+            if (p.pdl) pdl_wait();                  // negative rows may have been written by the previous minibatch
+            if (p.late_wait) { publish_predecessor(p); peer_wait_warp(p, (int)threadIdx.x); }
+            if (p.wait_step || p.pdl) fence_proxy_async();   // rows written with generic stores (here or by peers) are read by TMA next
             __syncwarp();
             if (negs) stage_negatives<L>(p, bv, s_neg, bar);
             if (LS && threadIdx.x == 31) bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, lut_bytes, bar);
@@ -760,13 +956,20 @@ force_batch_kernel(const BatchParams p) {
     }
     const int lane = threadIdx.x & 31;
     const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    // asynchronous-ring layouts: the lane groups' rings follow the staged negatives / table
+    const uint32_t ring_base = smem_u32(smem_raw) + 128u + neg_bytes + (LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u);
+    if (p.late_wait && !(negs || LS) && blockIdx.x == 0 && threadIdx.x == 0) {
+        // no staging warp in this launch: thread 0 of CTA 0 publishes the predecessor's step itself
+        if (p.pdl) pdl_wait();
+        publish_predecessor(p);
+    }
     if (PERSIST) {
         const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
         for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
-            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut);
+            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base);
     } else {
         const uint32_t t_base = gw * L::G;
-        if (t_base < bv.n_items) process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut);
+        if (t_base < bv.n_items) process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base);
     }
     // the CTA's shared memory must stay allocated until the bulk copies have landed
     if (negs || LS) mbar_wait(bar, 0);
@@ -866,8 +1069,10 @@ force_epoch_kernel(const EpochParams ep) {
 }
 
 // A launch with no rows on this rank still takes part in the exchange barrier; the epoch ends with
-// a wait for every peer's last step (then this replica is complete).  One CTA.
+// a wait for every peer's last step (then this replica is complete).  One CTA.  publish_step is
+// published BEFORE the wait (everything earlier in the stream is complete), signal_step after it.
 __global__ void peer_sync_kernel(const BatchParams p) {
+    publish_predecessor(p);
     peer_wait(p);
     peer_signal(p);
 }
@@ -917,6 +1122,31 @@ __global__ void shard_copy_kernel(float* table, float* staging, uint64_t first, 
             staging[i] = __ldcg(table + (size_t)row * dim + k);
         }
     }
+}
+
+// Order-independent 64-bit checksum of the live table: sum over (vertex v, component k) of
+// mix(v*dim + k, bits of X[v][k]) mod 2^64.  Any single differing bit changes the sum; used to
+// compare a multi-GPU replica / sharded table with a single-GPU run without moving the tables.
+__device__ __forceinline__ uint64_t checksum_mix(uint64_t pos, uint32_t bits) {
+    uint64_t z = (pos + 1) * 0x9E3779B97F4A7C15ULL + bits;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void checksum_kernel(const float* table, uint64_t n, uint32_t dim, uint32_t lg, uint32_t shard_rows,
+                                unsigned long long* out) {
+    const uint64_t total = n * dim;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint64_t v = i / dim;
+        const uint32_t k = (uint32_t)(i - v * dim);
+        const uint32_t row = shard_row((uint32_t)v, lg, shard_rows);
+        acc += checksum_mix(i, __float_as_uint(__ldcg(table + (size_t)row * dim + k)));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)acc);
 }
 
 // Counter-based draw for the device walk sampler (host mirror: oracle f2vo_counter_rand).

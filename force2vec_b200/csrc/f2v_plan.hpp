@@ -26,8 +26,6 @@ constexpr uint32_t kMinChunk = 8;
 // run the 8-rows-in-flight layout, for which a 16-edge item is two gather iterations), else 8.
 // A function of the batch size only, so every world size / epoch mode cuts hub rows identically.
 inline uint32_t default_min_chunk(uint32_t batch) { return batch <= 8192 ? 16u : kMinChunk; }
-// tuning override ("min_chunk" option; 0 = default_min_chunk)
-inline uint32_t& min_chunk_override() { static uint32_t v = 0; return v; }
 
 // Partial sums of a split row are folded in two levels: blocks of kFoldBlock consecutive chunks,
 // then the block sums.
@@ -125,7 +123,8 @@ inline void owned_rows(const uint64_t* rp, uint64_t first_row, uint64_t nrows, u
 // minibatch with little work is still cut into enough items to occupy `par` lane groups in one
 // wave and its critical path (the longest item) stays short.
 inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nrows, uint32_t batch,
-                            uint32_t chunk, uint32_t par, bool walk, int rank, int world, int assign, HostPlan& out) {
+                            uint32_t chunk, uint32_t par, bool walk, int rank, int world, int assign, HostPlan& out,
+                            uint32_t min_chunk = 0) {          // 0 = default_min_chunk(batch); per-engine tuning option
     const uint64_t nb = (nrows + batch - 1) / batch;
     std::vector<uint64_t> item_ptr(nb + 1, 0);
     std::vector<uint32_t> n_hub(nb, 0), n_slots(nb, 0);
@@ -146,7 +145,7 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
         uint64_t ch = chunk;
         if (par != 0 && bhi > blo) {
             const uint64_t c = (edges + par - 1) / par;
-            ch = std::min<uint64_t>(chunk, std::max<uint64_t>(std::min<uint64_t>(min_chunk_override() ? min_chunk_override() : default_min_chunk(batch), chunk), c));
+            ch = std::min<uint64_t>(chunk, std::max<uint64_t>(std::min<uint64_t>(min_chunk ? min_chunk : default_min_chunk(batch), chunk), c));
         }
         chunk_len[b] = ch;
         uint64_t cnt = 0, hubs = 0, slots = 0;

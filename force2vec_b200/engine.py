@@ -65,6 +65,17 @@ class Engine:
         check(lib().f2v_get_rows(self._h, first, nrows, _p(X)), "f2v_get_rows")
         return X
 
+    def checksum(self):
+        """64-bit device-side checksum of the live table (f2v_checksum)."""
+        h = C.c_uint64()
+        check(lib().f2v_checksum(self._h, C.byref(h)), "f2v_checksum")
+        return int(h.value)
+
+    def device_memory(self):
+        f, t = C.c_uint64(), C.c_uint64()
+        check(lib().f2v_device_memory(self._h, C.byref(f), C.byref(t)), "f2v_device_memory")
+        return int(f.value), int(t.value)
+
     def set_lut(self, table=None):
         t = host.build_lut() if table is None else np.ascontiguousarray(table, np.float32)
         check(lib().f2v_set_lut(self._h, _p(t), len(t)), "f2v_set_lut")

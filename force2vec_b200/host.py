@@ -121,3 +121,24 @@ def plan_build(rowptr, batch, chunk=64, walk=False, rank=0, world=1, first_row=0
         lib().f2v_free(q)
     return {"nb": nbv, "item_ptr": item_ptr, "n_hub": n_hub,
             "items": raw_i.view(ITEM_DTYPE)[:total], "hub": raw_h.view(HUB_DTYPE)[:total]}
+
+
+def rmat_csr_cached(scale, edge_factor=16, seed=1, cache_dir="/dev/shm"):
+    """rmat_csr with a page-cache copy under `cache_dir` (two .npy files, memory-mapped read-only),
+    so that the ranks of one node -- and successive commands on one box -- build the graph once
+    (multi-rank callers let one rank call this first, then a barrier, then the others)."""
+    import os
+    base = os.path.join(cache_dir, "f2v_rmat%d_ef%d_seed%d" % (scale, edge_factor, seed))
+    rp_path, ci_path = base + ".rowptr.npy", base + ".colids.npy"
+    if not (os.path.exists(rp_path) and os.path.exists(ci_path)):
+        rp, ci = rmat_csr(scale, edge_factor, seed)
+        try:
+            tmp = "%s.%d.tmp" % (base, os.getpid())
+            np.save(tmp + ".rp.npy", rp)
+            np.save(tmp + ".ci.npy", ci)
+            os.replace(tmp + ".ci.npy", ci_path)
+            os.replace(tmp + ".rp.npy", rp_path)       # rowptr last: its presence marks the pair complete
+        except OSError:
+            return rp, ci
+        del rp, ci
+    return np.load(rp_path, mmap_mode="r"), np.load(ci_path, mmap_mode="r")

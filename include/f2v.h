@@ -65,12 +65,25 @@ int f2v_sync(f2v_engine* e);
  * pageable memory work too, at lower PCIe throughput).                               */
 int f2v_host_alloc(void** p, uint64_t bytes);
 int f2v_host_free(void* p);
+/* Page-lock / release a range of caller-owned host memory in place (e.g. only the row range of a
+ * full-size table that a multi-GPU rank moves over its own PCIe link in f2v_run_epoch_host).   */
+int f2v_host_register(void* p, uint64_t bytes);
+int f2v_host_unregister(void* p);
+/* Free / total memory of the engine's device in bytes (reporting; either pointer may be NULL). */
+int f2v_device_memory(const f2v_engine* e, uint64_t* free_bytes, uint64_t* total_bytes);
 
 /* ---- state -----------------------------------------------------------------------
  * nCoordinates in / out (algorithms.h:54).  Host buffers of n*dim floats, row-major. */
 int f2v_set_embeddings(f2v_engine* e, const float* X_host);
 int f2v_get_embeddings(f2v_engine* e, float* X_host);
 int f2v_get_rows(f2v_engine* e, uint64_t first_row, uint64_t nrows, float* rows_host);
+/* Order-independent 64-bit checksum of the live table, computed on the device (sum over every
+ * (vertex, component) of a hash of its position and bit pattern): equal tables give equal sums, any
+ * differing bit changes it.  How a multi-GPU replica or a row-sharded table (remote shards are read
+ * over NVLink) is compared with a single-GPU run at sizes where moving the tables is not an option
+ * -- e.g. R-MAT 26 at d=128 (32 GiB), which the reference cannot run at all (algorithms.h:40,68:
+ * 32-bit n*DIM).  Synchronises.                                                               */
+int f2v_checksum(f2v_engine* e, uint64_t* checksum);
 /* The sigmoid table built on the host with the reference expression
  * (init_SM_TABLE, algorithms.cpp:757-764): `count` = 2048 entries; entry 2048 (the
  * reference's out-of-bounds read for v == 6.0f exactly) is defined as 1.0f.          */

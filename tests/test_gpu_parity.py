@@ -469,3 +469,50 @@ def test_dependent_launch_chaining_is_exact(model, bs, dim, batch):
         if ref is None:
             ref = X
         assert np.array_equal(ref, X), pdl
+
+
+@pytest.mark.parametrize("model,bs", MODEL_CASES)
+@pytest.mark.parametrize("dim,batch,scale,chunk", [(128, 512, 12, 0), (64, 1000, 12, 16), (128, 4096, 13, 8), (64, 64, 10, 0)])
+def test_async_ring_layouts_are_bit_identical(oracle, model, bs, dim, batch, scale, chunk):
+    """The asynchronous shared-memory-ring gather (RingL layouts: cp.async stages, neighbours and
+    per-vertex negatives in one stream, split rows taking their negatives after the fold) performs the
+    same operations in the same order as the register layouts: every variant gives the same bits, with
+    PDL chaining on, and agrees with the oracle."""
+    rp, ci = host.rmat_csr(scale, 16, 3)
+    s = 5
+    full, neg = _streams(oracle, model, bs, rp, ci, dim, 2, batch, s)
+    ref = None
+    for variant in (3 if dim == 128 else 1, 20, 21, 22, 23 if dim == 128 else 20, -1):
+        with _engine(rp, ci, dim, full["X0"], model) as e:
+            e.set_option("variant", variant)
+            for it in range(2):
+                if model == 7:
+                    e.set_walks(full["walks"][it])
+                e.set_negatives(neg[it])
+                e.run_epoch(model, batch, s, bs, LR, chunk=chunk)
+            X = e.get_embeddings()
+            h = e.checksum()
+        if ref is None:
+            ref, href = X, h
+            np.testing.assert_allclose(X, full["X"], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(ref, X), variant
+        assert h == href                                         # the device checksum sees the same table
+
+
+def test_checksum_detects_a_single_bit(cora):
+    rp, ci = cora
+    n = len(rp) - 1
+    X = host.RandStream(1).init_embeddings(5, n, 128)
+    with F.Engine(rp, ci, 128) as e:
+        e.set_embeddings(X)
+        a = e.checksum()
+        assert a == e.checksum()
+        Y = X.copy()
+        Y.view(np.uint32)[n // 2, 77] ^= 1
+        e.set_embeddings(Y)
+        b = e.checksum()
+        Y = X.copy()
+        Y[[3, 4]] = Y[[4, 3]]                                     # position matters, not only the multiset of values
+        e.set_embeddings(Y)
+        c = e.checksum()
+    assert len({a, b, c}) == 3

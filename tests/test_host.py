@@ -370,3 +370,50 @@ def test_binary_csr_cache_round_trip(tmp_path):
         host.load_csr(p)
     with pytest.raises(F.F2VError):
         host.load_csr(str(tmp_path / "missing.f2vcsr"))
+
+
+def test_threaded_loader_on_a_file_larger_than_1MiB(tmp_path, oracle):
+    """The entry lines of a file above 1 MiB are parsed by all host threads (pieces cut at line
+    boundaries, the first `cnt` entries of the file kept): symmetric file, trailing blank lines, more
+    entry lines than the size line declares, several OMP thread counts -- all equal to the serial
+    oracle loader and to the graph written."""
+    import subprocess
+    import sys
+    rp, ci = host.rmat_csr(14, 8, 7)
+    n = len(rp) - 1
+    p = str(tmp_path / "big.mtx")
+    host.write_mtx(p, rp, ci)
+    raw = open(p).read()
+    assert len(raw) > (1 << 20)
+    # surplus entries after the declared count (ignored) and trailing blank lines
+    raw += "1 2\n3 1\n\n\n\r\n"
+    open(p, "w").write(raw)
+    a = host.load_mtx(p)
+    assert np.array_equal(a[0], rp) and np.array_equal(a[1], ci)
+    b = oracle.load_mtx(p)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np; from force2vec_b200 import host; "
+            "rp, ci = host.load_mtx(%r); np.save(%r, rp); np.save(%r, ci)")
+    for nt in (1, 3, 8):
+        o1, o2 = str(tmp_path / ("rp%d.npy" % nt)), str(tmp_path / ("ci%d.npy" % nt))
+        subprocess.check_call([sys.executable, "-c", code % (ROOT, p, o1, o2)], env=dict(os.environ, OMP_NUM_THREADS=str(nt)))
+        assert np.array_equal(np.load(o1), rp) and np.array_equal(np.load(o2), ci), nt
+    # an entry out of range among the first `cnt` is an error with a message; a directory and a FIFO are refused
+    bad = raw.replace("\n", "\n%d 1\n" % (n + 5), 3)
+    open(p, "w").write(bad)
+    with pytest.raises(F.F2VError) as ei:
+        host.load_mtx(p)
+    assert "load_mtx" in str(ei.value)
+    with pytest.raises(F.F2VError) as ei:
+        host.load_mtx(str(tmp_path))
+    assert "regular file" in str(ei.value)
+    fifo = str(tmp_path / "fifo.mtx")
+    os.mkfifo(fifo)
+    with pytest.raises(F.F2VError):
+        host.load_mtx(fifo)
+
+
+def test_host_errors_carry_a_message(tmp_path):
+    with pytest.raises(F.F2VError) as ei:
+        host.load_csr(str(tmp_path / "nope.f2vcsr"))
+    assert "f2v_load_csr" in str(ei.value)
