@@ -334,6 +334,16 @@ struct VecL {
             acc[k] = r.x; acc[k + 1] = r.y;
         }
     }
+    // the same with the clamp known to be the identity (|d*d1| <= 5 proven by the caller): no FMNMX
+    __device__ static __forceinline__ void scale_acc(float (&acc)[NE], const float (&d)[NE], float d1, float w) {
+        const float2 d2 = make_float2(d1, d1), w2 = make_float2(w, w);
+#pragma unroll
+        for (int k = 0; k < NE; k += 2) {
+            const float2 t = __fmul2_rn(make_float2(d[k], d[k + 1]), d2);
+            float2 r = __fadd2_rn(make_float2(acc[k], acc[k + 1]), __fmul2_rn(w2, t));
+            acc[k] = r.x; acc[k + 1] = r.y;
+        }
+    }
 };
 
 // RingL<D,LPR,S,MINB>: the VecL<D,LPR,2> fragment layout, but gathered rows do not land in registers:
@@ -420,6 +430,10 @@ struct GenL {
         for (int k = 0; k < NE; k++)
             acc[k] = __fadd_rn(acc[k], __fmul_rn(w, fminf(fmaxf(__fmul_rn(d[k], d1), -5.0f), 5.0f)));
     }
+    __device__ static __forceinline__ void scale_acc(float (&acc)[NE], const float (&d)[NE], float d1, float w) {
+#pragma unroll
+        for (int k = 0; k < NE; k++) acc[k] = __fadd_rn(acc[k], __fmul_rn(w, __fmul_rn(d[k], d1)));
+    }
 };
 
 // ------------------------------------------------------------------ scalar pieces ------
@@ -465,10 +479,23 @@ __device__ __forceinline__ float pair_scalar(float r, float lr, float sd, const 
     return ATTR ? fmaf(-sd, sg, sd) : __fmul_rn(lr, sg);
 }
 
+// Option 5: can scale() (the clamp to +-5, algorithms.cpp:6-10) change any component of this pair?
+// |diff_k| <= sqrt(r) with r = sum diff^2, so |diff_k * d1| <= 2 sqrt(r)/(1+r) <= 1 for an attractive
+// pair and <= 2/(sqrt(r)(1+r)) <= 3.2 for a repulsive pair with r >= 0.25: the clamp is then the
+// identity and its 2*NE min/max instructions (a quarter of the pair's instructions) are skipped.
+// Anything else -- a close or identical negative (r < 0.25: the reference's NaN -> -5 quirk lives
+// here), a non-finite r -- takes the clamped path.  The decision is taken per warp (one vote).
+__device__ __forceinline__ bool may_clamp(float r, bool attr, bool valid) {
+    return valid && !(attr ? r < __int_as_float(0x7f800000) : (r >= 0.25f && r < __int_as_float(0x7f800000)));
+}
+
 template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void pair_apply(float (&acc)[L::NE], const float (&xp)[L::NE], const float (&d)[L::NE],
-                                           float sc, bool valid, float lr) {
-    if (MODEL == kTDist) L::clamp_acc(acc, d, sc, valid ? lr : 0.f);      // prev += STEP*scale(diff*d1)
+                                           float sc, bool valid, float lr, bool clampless = false) {
+    if (MODEL == kTDist) {                                                  // prev += STEP*scale(diff*d1)
+        if (clampless) L::scale_acc(acc, d, valid ? sc : 0.f, valid ? lr : 0.f);
+        else L::clamp_acc(acc, d, sc, valid ? lr : 0.f);
+    }
     else if (ATTR) L::axpy(acc, valid ? sc : 0.f, xp);                     // prev += c*x_j
     else L::sub_mul(acc, valid ? sc : 0.f, xp);                            // prev -= (STEP*d1)*sample
 }
@@ -484,7 +511,8 @@ __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&x
     float r = MODEL == kTDist ? L::diff_ss(d, xi, xp) : L::dot(xi, xp);
     r = group_sum<L::LPR>(r);
     const float sc = pair_scalar<MODEL, ATTR, LS>(r, lr, sd, lut);
-    pair_apply<L, MODEL, ATTR>(acc, xp, d, sc, valid, lr);
+    const bool clampless = MODEL == kTDist && !__any_sync(kFull, may_clamp(r, ATTR, valid));
+    pair_apply<L, MODEL, ATTR>(acc, xp, d, sc, valid, lr, clampless);
 }
 
 // Two pairs per group at once: the two lane-partial sums are reduced with a halving butterfly
@@ -508,8 +536,10 @@ __device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&
     const float mine = pair_scalar<MODEL, ATTR, LS>(keep, lr, sd, lut);
     const float other = __shfl_xor_sync(kFull, mine, H);
     const float s0 = hi ? other : mine, s1 = hi ? mine : other;
-    pair_apply<L, MODEL, ATTR>(acc, x0, d0, s0, v0, lr);
-    pair_apply<L, MODEL, ATTR>(acc, x1, d1, s1, v1, lr);
+    // (each half of the group holds the reduced r of ITS pair: one vote covers both pairs of every group)
+    const bool clampless = MODEL == kTDist && !__any_sync(kFull, may_clamp(keep, ATTR, hi ? v1 : v0));
+    pair_apply<L, MODEL, ATTR>(acc, x0, d0, s0, v0, lr, clampless);
+    pair_apply<L, MODEL, ATTR>(acc, x1, d1, s1, v1, lr, clampless);
 }
 
 __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(kFull, v); }
@@ -576,8 +606,11 @@ __device__ __forceinline__ float pair_scalar_rt(float r, bool attr, float lr, fl
 }
 template <class L, int MODEL>
 __device__ __forceinline__ void pair_apply_rt(float (&acc)[L::NE], const float (&xp)[L::NE], const float (&d)[L::NE],
-                                              float sc, bool valid, bool attr, float lr) {
-    if (MODEL == kTDist) L::clamp_acc(acc, d, sc, valid ? lr : 0.f);
+                                              float sc, bool valid, bool attr, float lr, bool clampless) {
+    if (MODEL == kTDist) {
+        if (clampless) L::scale_acc(acc, d, valid ? sc : 0.f, valid ? lr : 0.f);
+        else L::clamp_acc(acc, d, sc, valid ? lr : 0.f);
+    }
     else if (attr) L::axpy(acc, valid ? sc : 0.f, xp);
     else L::sub_mul(acc, valid ? sc : 0.f, xp);
 }
@@ -598,8 +631,9 @@ __device__ __forceinline__ void pair2_update_rt(float (&acc)[L::NE], const float
     const float mine = pair_scalar_rt<MODEL, LS>(keep, hi ? a1 : a0, lr, sd, lut);
     const float other = __shfl_xor_sync(kFull, mine, H);
     const float s0 = hi ? other : mine, s1 = hi ? mine : other;
-    pair_apply_rt<L, MODEL>(acc, x0, d0, s0, v0, a0, lr);
-    pair_apply_rt<L, MODEL>(acc, x1, d1, s1, v1, a1, lr);
+    const bool clampless = MODEL == kTDist && !__any_sync(kFull, may_clamp(keep, hi ? a1 : a0, hi ? v1 : v0));
+    pair_apply_rt<L, MODEL>(acc, x0, d0, s0, v0, a0, lr, clampless);
+    pair_apply_rt<L, MODEL>(acc, x1, d1, s1, v1, a1, lr, clampless);
 }
 
 // The asynchronous gather (RingL layouts).  An item's rows form ONE stream: its cntA attractive rows

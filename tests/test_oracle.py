@@ -4,7 +4,7 @@ made by tests/golden/make_golden.py), the reference's own sigmoid table and libc
 import os
 import numpy as np
 import pytest
-from conftest import GOLDEN, gkey
+from conftest import GOLDEN, ROOT, gkey
 
 
 def test_rand_stream_matches_libc_golden(oracle):
@@ -141,3 +141,28 @@ def test_counter_walks_deterministic(oracle, cora):
     c = oracle.walks_counter(7, 4, rp, ci)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     assert a.max() < len(rp) - 1
+
+
+def test_evalscores_reproduce_the_reference_scripts():
+    """tools/evalscores.py is pinned to the reference's own evaluation scripts: for the seeds the
+    golden generator used (tests/golden/make_eval_golden.py ran the unmodified
+    performancescores/runlinkpredict.py and runnodeclassclust.py on the reference's shipped golden
+    embedding), its reference-protocol functions give the scripts' printed accuracy / F1 values."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import evalscores as E
+    gold = json.load(open(os.path.join(GOLDEN, "ref_eval_scores.json")))
+    X32 = np.load(os.path.join(GOLDEN, "shipped_cora_F2VNS384D128IT1200NS5.npz"))["X"]
+    # the scripts parse the .embd text (6 significant digits) into float64: re-render the fixture's
+    # float32 values the same way (FLT_DIG = 6: the text round-trips)
+    X = np.array([float("%.6g" % v) for v in X32.ravel()]).reshape(X32.shape)
+    labels = E.read_labels(os.path.join(GOLDEN, "cora.nodes.labels"), X.shape[0])
+    for seed, want in gold["seeds"].items():
+        lp = E.link_prediction_reference(os.path.join(GOLDEN, "cora.mtx"), X, int(seed))
+        for k, v in want["link_prediction"].items():
+            assert abs(lp[k] - v) < 1e-9, (seed, k, lp[k], v)
+        nc = E.node_classification_reference(X, labels, int(seed))
+        for tf, sc in want["node_classification"].items():
+            for k, v in sc.items():
+                assert abs(nc[float(tf)][k] - v) < 1e-9, (seed, tf, k, nc[float(tf)][k], v)
