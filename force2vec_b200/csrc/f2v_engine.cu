@@ -247,6 +247,8 @@ struct f2v_engine {
     int variant = -1;                        // d=128 lane layout: -1 auto, see launch_batch
     int neg_smem = 1;
     int epoch_ctas = 0;                      // persistent epoch kernel: CTAs per SM (0 = as many as fit)
+    int auto_flow = 0;                       // epoch mode 0: batches up to this size run the dataflow epoch kernel (0 = never)
+    bool flow_used = false;                  // a dataflow launch reports a wait time-out through d_done[1]
     uint32_t min_chunk = 0;                  // lower bound of the adaptive hub chunk (0 = default_min_chunk(batch))
     int par = 9472;                          // adaptive-chunk target: 148 SMs x 64 lane groups (0 = fixed chunk)
     uint64_t launches = 0;
@@ -262,6 +264,8 @@ struct f2v_engine {
     uint64_t* d_flags = nullptr;             // local flag page, kMaxWorld * kFlagStride u64
     uint32_t* d_done = nullptr;
     uint32_t* d_bar = nullptr;               // grid-barrier counter of the persistent epoch kernel
+    uint32_t* d_flow = nullptr;              // dataflow epoch: [ticket (128-byte line)] [cnt nb] [done nb]
+    uint64_t flow_cap = 0;
     uint64_t step_id = 0;                    // minibatch steps published so far (same on every rank)
     // NVLink multicast (NVLS) exchange: tables + flag page live in one VMM allocation bound to a
     // multicast object shared by all ranks; a store through the multicast mapping lands everywhere
@@ -562,6 +566,52 @@ static cudaError_t launch_epoch(int model, const EpochParams& ep, cudaStream_t s
     return launch_epoch_m<GenL<32>>(model, ep, st, sm_count, cps, grid, query);
 }
 
+
+// ---- dataflow epoch kernel (epoch mode 2): ordinary launch, grid = SMs x resident CTAs
+template <class L, int MODEL>
+static cudaError_t launch_flow_k(const FlowParams& fp, cudaStream_t st, int sm_count) {
+    auto kern = force_flow_kernel<L, MODEL>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const unsigned per_cta = kWarpsPerCta * L::G;
+    const unsigned want = (fp.total_items + per_cta - 1) / per_cta;
+    const unsigned grid = std::max(1u, std::min(want, (unsigned)(sm_count * per_sm)));
+    kern<<<grid, kWarpsPerCta * 32, 0, st>>>(fp);
+    return cudaGetLastError();
+}
+template <class L>
+static cudaError_t launch_flow_m(int model, const FlowParams& fp, cudaStream_t st, int sm_count) {
+    switch (model) {
+    case kTDist: return launch_flow_k<L, kTDist>(fp, st, sm_count);
+    case kSigmoid: return launch_flow_k<L, kSigmoid>(fp, st, sm_count);
+    default: return launch_flow_k<L, kWalk>(fp, st, sm_count);
+    }
+}
+static cudaError_t launch_flow(int model, const FlowParams& fp, cudaStream_t st, int sm_count, int variant) {
+    const uint32_t dim = fp.p.dim;
+    switch (dim) {
+    case 32: return launch_flow_m<VecL<32, 8, 8>>(model, fp, st, sm_count);
+    case 64: return variant == 0 ? launch_flow_m<VecL<64, 8, 4>>(model, fp, st, sm_count)
+                                 : launch_flow_m<VecL<64, 8, 2, 4>>(model, fp, st, sm_count);
+    case 128:
+        switch (variant) {
+        case 8: return launch_flow_m<VecL<128, 16, 2, 5>>(model, fp, st, sm_count);
+        case 11: return launch_flow_m<VecL<128, 16, 8, 2>>(model, fp, st, sm_count);
+        default: return launch_flow_m<VecL<128, 16, 2, 4>>(model, fp, st, sm_count);
+        }
+    case 256: return launch_flow_m<VecL<256, 32, 4>>(model, fp, st, sm_count);
+    default: break;
+    }
+    if (dim <= 32) return launch_flow_m<GenL<1>>(model, fp, st, sm_count);
+    if (dim <= 64) return launch_flow_m<GenL<2>>(model, fp, st, sm_count);
+    if (dim <= 128) return launch_flow_m<GenL<4>>(model, fp, st, sm_count);
+    if (dim <= 256) return launch_flow_m<GenL<8>>(model, fp, st, sm_count);
+    if (dim <= 512) return launch_flow_m<GenL<16>>(model, fp, st, sm_count);
+    return launch_flow_m<GenL<32>>(model, fp, st, sm_count);
+}
+
 static bool bulk_ok(const f2v_engine* e, uint32_t s, int bs_mode) {
     if (bs_mode != 0 || s == 0 || !e->neg_smem) return false;
     if (!(e->dim == 32 || e->dim == 64 || e->dim == 128 || e->dim == 256)) return false;
@@ -749,6 +799,7 @@ int f2v_destroy(f2v_engine* e) {
     cudaFree(e->epoch_plan.d_items); cudaFree(e->epoch_plan.d_hub); cudaFree(e->epoch_plan.d_item_ptr);
     cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub); cudaFree(e->step_plan.d_item_ptr);
     cudaFree(e->d_bar);
+    cudaFree(e->d_flow);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_rows) cudaEventDestroy(e->ev_rows);
@@ -802,9 +853,12 @@ int f2v_set_stream(f2v_engine* e, void* cuda_stream) {
 
 // Multi-GPU: did a launch give up waiting for a peer's exchange step?  (stream already synchronised)
 static int check_exchange(f2v_engine* e) {
-    if (!e->peer_mode || !e->d_done) return F2V_OK;
+    if ((!e->peer_mode && !e->flow_used) || !e->d_done) return F2V_OK;
     uint32_t flag = 0;
     CU(cudaMemcpy(&flag, e->d_done + 1, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag == 2)
+        return fail(F2V_ERR_STATE, "dataflow epoch: a warp waited more than 20 s for a minibatch to complete (internal error); "
+                                   "the tables are not valid");
     if (flag)
         return fail(F2V_ERR_STATE, "multi-GPU exchange timed out after %d ms: a peer rank did not publish its step "
                                    "(did every rank issue the same calls?); the tables are not valid", e->exchange_timeout_ms);
@@ -1033,8 +1087,12 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     if (r) return r;
     if (e->shard_mode && e->epoch_mode != 0) return fail(F2V_ERR_STATE, "row-sharded engines run epoch mode 0");
     const int order = e->order >= 0 ? e->order : (e->peer_mode ? 1 : 0);
+    // dataflow epoch (mode 2, or mode 0 = automatic at small batches): single-GPU engines, at least two minibatches
+    const bool flow = e->world == 1 && nb >= 2 && nb * (uint64_t)batch < 0xffffffffull &&
+                      (e->epoch_mode == 2 || (e->epoch_mode == 0 && e->auto_flow && batch <= (uint32_t)e->auto_flow));
     r = build_plan(e, e->epoch_plan, 0, e->n, batch, chunk, (uint32_t)e->par, model == F2V_WALK, e->rank, e->world,
-                   (e->peer_mode ? kAssignBalanced : kAssignSlices) | (order == 1 ? kOrderLightFirst : 0) | (order == 2 ? kOrderInterleave : 0));
+                   flow ? kPlanFlow
+                        : ((e->peer_mode ? kAssignBalanced : kAssignSlices) | (order == 1 ? kOrderLightFirst : 0) | (order == 2 ? kOrderInterleave : 0)));
     if (r) return r;
     const Plan& pl = e->epoch_plan;
     float* Xnew = e->d_X[1 - e->cur];
@@ -1066,6 +1124,43 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
             p.peer_flag[k] = e->peer_flags[r] + (size_t)e->rank * kFlagStride;
             k++;
         }
+    }
+    if (flow) {
+        // dataflow epoch: one ordinary launch, minibatches overlap, readers wait for their writers only
+        const uint64_t words = 32 + 2 * nb;
+        if (e->flow_cap < words || !e->d_flow) {
+            if (e->d_flow) CU(cudaFree(e->d_flow));
+            e->d_flow = nullptr; e->flow_cap = 0;
+            CU(cudaMalloc((void**)&e->d_flow, sizeof(uint32_t) * words));
+            e->flow_cap = words;
+        }
+        CU(cudaMemsetAsync(e->d_flow, 0, sizeof(uint32_t) * words, e->stream));
+        FlowParams fp{};
+        fp.p = p;
+        fp.p.items = pl.d_items; fp.p.hub = pl.d_hub; fp.p.neg = e->d_neg + e->neg_off;
+        fp.p.n_items = (uint32_t)pl.item_ptr[nb];
+        fp.p.neg_in_smem = 0;                    // a CTA works on several minibatches at once: negatives come from L2
+        fp.p.pdl = 0; fp.p.late_wait = 0; fp.p.wait_step = 0; fp.p.signal_step = 0;
+        fp.p.flow_cnt = e->d_flow + 32;
+        fp.p.flow_done = e->d_flow + 32 + nb;
+        fp.p.flow_batch = batch; fp.p.flow_nb = (uint32_t)nb; fp.p.flow_n = (uint32_t)e->n;
+        fp.p.timeout_ns = 20ull * 1000000000ull;     // a wait this long is a bug: report it, do not hang the GPU
+        if (!e->d_done) { CU(cudaMalloc((void**)&e->d_done, sizeof(uint32_t) * 32)); CU(cudaMemsetAsync(e->d_done, 0, sizeof(uint32_t) * 32, e->stream)); }
+        fp.p.timed_out = e->d_done + 1;
+        fp.total_items = (uint32_t)pl.item_ptr[nb];
+        fp.neg_stride = (uint32_t)W;
+        fp.ticket = e->d_flow;
+        if (fp.total_items) {
+            CU(launch_flow(model, fp, e->stream, e->sm_count, e->variant));
+            e->launches++;
+        }
+        if (X_out_host)
+            CU(cudaMemcpyAsync(X_out_host, Xnew, sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(e->ev1, e->stream));
+        e->ev_valid = true;
+        e->flow_used = true;
+        e->cur = 1 - e->cur;
+        return F2V_OK;
     }
     if (e->epoch_mode == 1 && nb >= 1 && !(e->world > 1 && !e->peer_mode)) {
         // one persistent cooperative launch for the whole epoch
@@ -1126,7 +1221,8 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
             // monotone).
             p.publish_step = p.wait_step;
             p.signal_step = 0;
-            p.late_wait = 1;
+            p.late_wait = p.pdl != 0;        // the first (ordinary) launch waits at kernel entry: its own rows of the
+                                             // current table may just have been uploaded / broadcast by a peer
             if (p.n_items) {
                 CU(launch_batch(model, p, e->stream, e->sm_count));
                 e->launches++;
@@ -1262,7 +1358,7 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
 
 int f2v_set_epoch_mode(f2v_engine* e, int mode) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
-    if (mode != 0 && mode != 1) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
+    if (mode != 0 && mode != 1 && mode != 2) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
     e->epoch_mode = mode;
     return F2V_OK;
 }
@@ -1281,6 +1377,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "exchange_timeout_ms")) e->exchange_timeout_ms = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "sharded")) e->want_shard = value != 0;
     else if (!strcmp(name, "epoch_ctas")) e->epoch_ctas = (int)value;
+    else if (!strcmp(name, "auto_flow")) e->auto_flow = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "min_chunk")) e->min_chunk = (uint32_t)std::max<int64_t>(0, value);   // part of the plan cache key
     else return fail(F2V_ERR_ARG, "unknown option %s", name);
     return F2V_OK;

@@ -646,7 +646,7 @@ extern "C" int f2v_plan_build(const uint64_t* rowptr, uint64_t first_row, uint64
                               uint32_t chunk, uint32_t par, int walk, int rank, int world, int assign, uint64_t* nb,
                               uint64_t** item_ptr, uint32_t** n_hub, void** items, void** hub) {
     if (!rowptr || !nb || !item_ptr || !n_hub || !items || !hub || batch == 0 || world < 1 || rank < 0 ||
-        rank >= world || chunk == 0 || assign < 0 || assign > 7)
+        rank >= world || chunk == 0 || assign < 0 || assign > 15)
         return f2v::host_fail(F2V_ERR_ARG, "f2v_plan_build: bad argument or malformed input");
     f2v::HostPlan hp;
     f2v::build_host_plan(rowptr, first_row, nrows, batch, chunk, par, walk != 0, rank, world, assign, hp);

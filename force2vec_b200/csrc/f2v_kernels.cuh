@@ -105,6 +105,14 @@ struct BatchParams {
     // minibatch) is still draining; everything the predecessor can have written is read only after
     // griddepcontrol.wait.  pdl = 2: the item's own row (from the current table, last written one
     // epoch ago) is also fetched before the wait.
+    // ---- dataflow epoch (f2v_set_epoch_mode 2): one launch per epoch, minibatches overlap; a warp
+    // waits only until the minibatches that wrote the rows it is about to read are complete.
+    // flow_done[b] != 0: every row of minibatch b has been stored; flow_cnt[b]: rows finished so far.
+    const uint32_t* flow_done;
+    uint32_t* flow_cnt;
+    uint32_t flow_batch;                 // rows per minibatch
+    uint32_t flow_nb;                    // minibatches per epoch
+    uint32_t flow_n;                     // rows of the table
     int pdl;
     int late_wait;        // multi-GPU: 1 = every warp waits for the peers' flags after its dependency wait
                           // (PDL-chained launches); 0 = one CTA-wide wait at kernel entry
@@ -217,16 +225,25 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// Spin until *f >= want, or until the exchange time-out expires (checked every 256 polls).
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until *f >= want, or until the exchange time-out expires (checked every 256 polls).  The polls
+// are relaxed loads (an acquire per poll would put a system-scope fence into the spin loop of every
+// waiting warp); ONE acquire load after the value has been seen orders the row reads that follow.
 __device__ __forceinline__ void wait_flag(const uint64_t* f, uint64_t want, uint64_t timeout_ns, uint32_t* timed_out) {
     uint64_t t0 = 0;
-    for (uint32_t spins = 0; ld_acquire_sys(f) < want; spins++) {
+    for (uint32_t spins = 0; ld_relaxed_sys(f) < want; spins++) {
+        if ((spins & 15u) == 15u) __nanosleep(32);
         if ((spins & 255u) == 255u && timeout_ns) {
             const uint64_t now = global_timer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > timeout_ns) { if (timed_out) atomicExch(timed_out, 1u); return; }
         }
     }
+    (void)ld_acquire_sys(f);
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -544,6 +561,46 @@ __device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&
 
 __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(kFull, v); }
 
+
+// ------------------------------------------------------------------ dataflow epoch -----
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Called by the whole warp before it gathers rows of the NEXT table: `need` = 1 + the largest vertex
+// id below the split among the ids it is about to read (0 = none); rows [0, rows_ok) are known to be
+// complete (a per-warp register, monotone over the epoch).  Minibatches finish roughly in order and
+// items are handed out in order, so the wait is "every minibatch up to the one holding row need-1
+// is complete": the lanes poll 32 consecutive completion flags per load.  Everything a warp can wait
+// for belongs to items handed out before its own, i.e. to warps that are running: no deadlock; the
+// time-out only turns a programming error into a reported failure instead of a hung GPU.
+__device__ __forceinline__ void flow_wait(const BatchParams& p, uint32_t need, uint32_t& rows_ok, int lane) {
+    if (need <= rows_ok) return;
+    uint32_t F = rows_ok / p.flow_batch;                 // minibatches known complete
+    const uint32_t want = (need - 1) / p.flow_batch;     // must become < F
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0; F <= want; spins++) {
+        const uint32_t b = F + (uint32_t)lane;
+        const uint32_t ok = b < p.flow_nb ? ld_acquire_gpu(p.flow_done + b) : 0u;
+        const uint32_t mask = __ballot_sync(kFull, ok != 0u);
+        const uint32_t lead = mask == kFull ? 32u : (uint32_t)__ffs((int)~mask) - 1u;
+        F += lead;
+        if (lead == 0u) {
+            __nanosleep(64);
+            if ((spins & 1023u) == 1023u && p.timeout_ns) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > p.timeout_ns) { if (p.timed_out && lane == 0) atomicExch(p.timed_out, 2u); break; }
+            }
+        }
+    }
+    rows_ok = max(rows_ok, min(F * p.flow_batch, p.flow_n));
+}
+
 // Every group gathers its own `cnt` rows named by idx[0..cnt) (in order) and folds them into
 // its acc.  Indices are fetched LPR at a time per group (coalesced) and broadcast inside the
 // group by shuffle; U row loads per group (G*U per warp) are in flight.
@@ -551,7 +608,7 @@ template <class L, int MODEL, bool ATTR, bool LS>
 __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const uint32_t* __restrict__ idx, uint32_t cnt,
                                              uint32_t self, const BatchParams& p, uint32_t split, float sd, int l,
-                                             const float* __restrict__ lut, bool have_first = false,
+                                             const float* __restrict__ lut, uint32_t& rows_ok, bool have_first = false,
                                              uint32_t first = 0) {
     constexpr int LPR = L::LPR, U = L::U;
     const size_t rs = L::stride(p.dim);
@@ -563,6 +620,8 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
         // (ld.global.cg, not the non-coherent path: negative and walk indices are rewritten between
         // epochs, and with dependent launches an SM's L1 can outlive a launch boundary)
         uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldcg(idx + base + l) : self);
+        if (p.flow_done != nullptr)                      // dataflow epoch: the writers of the rows below the split must be done
+            flow_wait(p, __reduce_max_sync(kFull, mine < split ? mine + 1u : 0u), rows_ok, (int)(threadIdx.x & 31));
         mine = table_row(p, mine, split);                // row of the combined table
         for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
@@ -650,7 +709,7 @@ __device__ __forceinline__ void gather_stream(float (&acc)[L::NE], const float (
                                               const uint32_t* __restrict__ idxA, uint32_t cntA,
                                               const uint32_t* __restrict__ idxB, uint32_t cntB,
                                               uint32_t self, const BatchParams& p, uint32_t split, float sd, int l,
-                                              const float* __restrict__ lut, uint32_t ring, bool have_first,
+                                              const float* __restrict__ lut, uint32_t ring, uint32_t& rows_ok, bool have_first,
                                               uint32_t first) {
     constexpr int LPR = L::LPR, S = L::kStages, VPL = L::VPL;
     constexpr uint32_t RB = L::kRowBytes;
@@ -666,8 +725,12 @@ __device__ __forceinline__ void gather_stream(float (&acc)[L::NE], const float (
         uint32_t j = self;
         if (P < cntA) j = __ldcg(idxA + P);
         else if (P < cnt) j = __ldcg(idxB + (P - cntA));
+        if (p.flow_done != nullptr)
+            flow_wait(p, __reduce_max_sync(kFull, j < split ? j + 1u : 0u), rows_ok, (int)(threadIdx.x & 31));
         return table_row(p, j, split);
     };
+    if (have_first && p.flow_done != nullptr)
+        flow_wait(p, __reduce_max_sync(kFull, first < split ? first + 1u : 0u), rows_ok, (int)(threadIdx.x & 31));
     uint32_t ids_cur = have_first ? table_row(p, first, split) : load_ids(0);   // block of the copy pointer
     uint32_t ids_nxt = cnt_max > (uint32_t)LPR ? load_ids(LPR) : 0u;             // the block after it
     uint32_t blk = 0;                                                            // block index of ids_cur
@@ -765,15 +828,16 @@ __device__ __forceinline__ void publish_predecessor(const BatchParams& p) {
 template <class L, int MODEL, bool LS>
 __device__ __forceinline__ void process_items(const BatchParams& p, const BatchVar& bv, uint32_t t_base,
                                               const float* s_neg, uint64_t* neg_bar, uint32_t neg_parity, int lane,
-                                              const float* __restrict__ lut, uint32_t ring_base = 0) {
+                                              const float* __restrict__ lut, uint32_t ring_base, uint32_t& rows_ok) {
     constexpr int NE = L::NE, LPR = L::LPR;
     constexpr bool kRing = L::kStages > 0;
     const int g = lane / LPR, l = lane % LPR;
     const size_t rs = L::stride(p.dim);
     const uint32_t t = t_base + g;
-    const bool active = t < bv.n_items;
+    bool active = t < bv.n_items;
     Item it{0, 0, 0};
     if (active) it = bv.items[t];
+    if (it.v == kNoVertex) { active = false; it.v = (uint32_t)bv.lo; }   // padding item of a dataflow plan
     const bool is_chunk = (it.len & kChunkFlag) != 0;
     const uint32_t len = it.len & ~kChunkFlag;
     const uint32_t v = it.v;
@@ -802,8 +866,10 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     // the dependent launch is released only after this one's own wait: when minibatch b+1 starts,
     // minibatch b-1 is therefore complete
     if (p.pdl == 2) { pdl_wait(); pdl_launch_dependents(); }
-    // multi-GPU: rows of the next table written by the peers' previous minibatch (the item's own row
-    // comes from the current table, which nobody writes during this epoch)
+    // multi-GPU, PDL-chained launch: rows of the next table written by the peers' previous minibatch.
+    // (The item's own row comes from the current table, which nobody writes between the epoch's first
+    // launch -- an ordinary launch that waits at kernel entry, because an upload / broadcast may just
+    // have rewritten the current table -- and the epoch's end.)
     if (p.late_wait) peer_wait_warp(p, lane);
     float sd = 0.f;
     if (MODEL != kTDist) {
@@ -820,9 +886,9 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     uint32_t ring = 0;
     if constexpr (kRing) {
         ring = ring_base + (uint32_t)(((threadIdx.x >> 5) * L::G + g) * L::kGroupBytes);
-        gather_stream<L, MODEL, LS>(acc, xi, nbr, nbr_cnt, nidx, negB, v, p, bv.split, sd, l, lut, ring, early_idx, first);
+        gather_stream<L, MODEL, LS>(acc, xi, nbr, nbr_cnt, nidx, negB, v, p, bv.split, sd, l, lut, ring, rows_ok, early_idx, first);
     } else {
-        gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, early_idx, first);
+        gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, rows_ok, early_idx, first);
     }
 
     // split rows: publish this chunk's partial sum; the last chunk of a fold block (kFoldBlock
@@ -888,9 +954,9 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
         // follow the fold (the chunk that finished the row)
         if (any_chunk)
             gather_stream<L, MODEL, LS>(acc, xi, nbr, 0u, nidx, (is_chunk && finish) ? p.s : 0u, v, p, bv.split, sd, l, lut,
-                                        ring, false, 0u);
+                                        ring, rows_ok, false, 0u);
     } else {
-        gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, bv.split, sd, l, lut);
+        gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, bv.split, sd, l, lut, rows_ok);
     }
     if (finish) {
         if (MODEL == kTDist || is_chunk) {
@@ -906,6 +972,18 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
         } else {
             L::store_g(p.out + off, acc, l, p.dim);
             for (uint32_t r = 0; r < p.n_store; r++) L::store_g(p.peer_out[r] + off, acc, l, p.dim);
+        }
+    }
+    if (p.flow_done != nullptr) {
+        // dataflow epoch: count this warp's finished rows into their minibatch (all lane groups of a warp
+        // work on the same one); whoever completes it publishes the flag the readers of its rows poll
+        __threadfence();
+        const uint32_t k = (uint32_t)__popc(__ballot_sync(kFull, finish && l == 0));
+        if (lane == 0 && k != 0u) {
+            const uint32_t b = v / p.flow_batch;
+            const uint32_t rows_b = min(p.flow_batch, p.flow_n - b * p.flow_batch);
+            const uint32_t old = atomicAdd(p.flow_cnt + b, k);
+            if (old + k == rows_b) { __threadfence(); st_release_gpu(const_cast<uint32_t*>(p.flow_done) + b, 1u); }
         }
     }
 }
@@ -992,6 +1070,7 @@ force_batch_kernel(const BatchParams p) {
     const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     // asynchronous-ring layouts: the lane groups' rings follow the staged negatives / table
     const uint32_t ring_base = smem_u32(smem_raw) + 128u + neg_bytes + (LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u);
+    uint32_t rows_ok = 0;
     if (p.late_wait && !(negs || LS) && blockIdx.x == 0 && threadIdx.x == 0) {
         // no staging warp in this launch: thread 0 of CTA 0 publishes the predecessor's step itself
         if (p.pdl) pdl_wait();
@@ -1000,10 +1079,10 @@ force_batch_kernel(const BatchParams p) {
     if (PERSIST) {
         const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
         for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
-            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base);
+            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base, rows_ok);
     } else {
         const uint32_t t_base = gw * L::G;
-        if (t_base < bv.n_items) process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base);
+        if (t_base < bv.n_items) process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base, rows_ok);
     }
     // the CTA's shared memory must stay allocated until the bulk copies have landed
     if (negs || LS) mbar_wait(bar, 0);
@@ -1070,6 +1149,7 @@ force_epoch_kernel(const EpochParams ep) {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
+    uint32_t rows_ok = 0;
     if (p.n_peers && ep.step0) {
         // rows the peers stored during the previous epoch's last minibatch
         if (threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
@@ -1094,11 +1174,54 @@ force_epoch_kernel(const EpochParams ep) {
             stage_negatives<L>(p, bv, s_neg, bar_neg);
         }
         for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
-            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar_neg, b & 1u, lane, lut);
+            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar_neg, b & 1u, lane, lut, 0u, rows_ok);
         // the staged rows must have landed before shared memory is reused / the CTA exits
         if (negs) mbar_wait(bar_neg, b & 1u);
         if (b + 1 < ep.nb || p.n_peers)
             grid_barrier(p, ep.bar_count, (b + 1) * gridDim.x, ep.step0 + b + 1);
+    }
+}
+
+
+// ------------------------------------------------------------------ dataflow epoch kernel
+// The whole epoch in ONE ordinary launch with no barrier at all (f2v_set_epoch_mode 2).  The epoch's
+// items (every minibatch's list, padded so that a warp's lane groups share a minibatch) are handed
+// out in order through one ticket counter; a warp that is about to read rows of the next table waits
+// -- flow_wait() -- only until the minibatches that write those rows are complete.  At the reference's
+// batch sizes (256 / 384) almost no row read depends on the few minibatches in flight, so thousands
+// of dependent minibatches overlap instead of paying a launch + drain (or a grid barrier) each, with
+// exactly the reference's Jacobi semantics: a row below the minibatch's split is read from the next
+// table after its writer finished, any other row from the current table, which nobody writes.
+// Shared negatives (bs=0) are gathered from L2 here (a CTA works on several minibatches at once).
+struct FlowParams {
+    BatchParams p;               // items / hub: the epoch's plan; neg: the epoch's negative stream
+    uint32_t total_items;
+    uint32_t neg_stride;         // negative indices per minibatch
+    uint32_t* ticket;            // next item (zeroed before the launch)
+};
+template <class L, int MODEL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, L::MINB)
+force_flow_kernel(const FlowParams fp) {
+    const BatchParams& p = fp.p;
+    const int lane = threadIdx.x & 31;
+    uint32_t rows_ok = 0;
+    for (;;) {
+        uint32_t t_base = 0;
+        if (lane == 0) t_base = atomicAdd(fp.ticket, (uint32_t)L::G);
+        t_base = __shfl_sync(kFull, t_base, 0);
+        if (t_base >= fp.total_items) break;
+        // minibatch of this warp's items: that of its first item (padding keeps a warp inside one minibatch;
+        // the first item of a group of kFlowPad is never a padding item)
+        const uint32_t v0 = p.items[t_base].v;
+        const uint32_t b = v0 / p.flow_batch;
+        BatchVar bv;
+        bv.items = p.items;
+        bv.hub = p.hub;
+        bv.n_items = fp.total_items;
+        bv.split = b * p.flow_batch;
+        bv.lo = bv.split;
+        bv.neg = p.neg + (size_t)b * fp.neg_stride;
+        process_items<L, MODEL, false>(p, bv, t_base, nullptr, nullptr, 0, lane, p.lut, 0u, rows_ok);
     }
 }
 

@@ -44,6 +44,7 @@ struct HostPlan {
     std::vector<Item> items;
     std::vector<HubInfo> hub;
     uint32_t max_slots = 0;
+    uint64_t total_slots = 0;         // hub partial-sum slots of all minibatches together
 };
 
 // Row slice of minibatch b owned by `rank`: the minibatch [blo, bhi) is cut into `world`
@@ -77,6 +78,14 @@ constexpr int kOrderLightFirst = 2;
 // their counts.  Light rows are almost pure output traffic; spreading them over the launch keeps
 // the multi-GPU row stores below the NVLink egress rate instead of bursting.
 constexpr int kOrderInterleave = 4;
+// Flag OR-ed into `assign`: plan for the dataflow epoch kernel (one launch per epoch, minibatches
+// overlap and wait only for the rows they read).  Every minibatch's item list is padded to a multiple
+// of kFlowPad items with inactive items (v = kNoVertex), so the lane groups of one warp always work on
+// the same minibatch, and hub partial-sum slots are numbered over the whole epoch (several
+// minibatches are in flight at once): max_slots = slots of the epoch.
+constexpr int kPlanFlow = 8;
+constexpr uint32_t kFlowPad = 4;
+constexpr uint32_t kNoVertex = 0xffffffffu;
 constexpr uint64_t kRowCost = 6;      // own row + ~5 negatives per vertex
 
 // Rows of minibatch b owned by `rank`, ascending.  world == 1: the whole minibatch.
@@ -154,15 +163,20 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
             cnt += c;
             if (c > 1) { hubs += c; slots += hub_slots(c); }
         }
+        if (assign & kPlanFlow) cnt = (cnt + kFlowPad - 1) / kFlowPad * kFlowPad;
         item_ptr[b + 1] = cnt;
         n_hub[b] = (uint32_t)hubs;
         n_slots[b] = (uint32_t)slots;
     }
     uint32_t max_slots = 0;
+    std::vector<uint64_t> slot_base(nb + 1, 0);
     for (uint64_t b = 0; b < nb; b++) {
         item_ptr[b + 1] += item_ptr[b];
         max_slots = std::max(max_slots, n_slots[b]);
+        slot_base[b + 1] = slot_base[b] + n_slots[b];
     }
+    if (assign & kPlanFlow) max_slots = (uint32_t)std::min<uint64_t>(slot_base[nb], 0xffffffffull);
+    out.total_slots = slot_base[nb];
     const uint64_t total = item_ptr[nb];
     std::vector<Item> items(total ? total : 1);
     std::vector<HubInfo> hub(total ? total : 1);
@@ -173,7 +187,7 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
         HubInfo* hb = hub.data() + item_ptr[b];
         const uint64_t ch = chunk_len[b];
         uint64_t k = 0;
-        uint32_t slot = 0;
+        uint32_t slot = (assign & kPlanFlow) ? (uint32_t)slot_base[b] : 0u;
         for (uint32_t v : rows) {                      // hub chunks
             uint64_t deg = rp[v + 1] - rp[v], nc = nchunks_of(deg, ch);
             if (nc <= 1) continue;
@@ -222,6 +236,12 @@ inline void build_host_plan(const uint64_t* rp, uint64_t first_row, uint64_t nro
                 }
                 for (uint64_t q = k; q < end; q++) hb[q] = HubInfo{0, 1, 0, it[q].len};
             }
+        }
+        if (assign & kPlanFlow) {                      // inactive padding items at the end of the minibatch
+            const uint64_t end = item_ptr[b + 1] - item_ptr[b];
+            uint64_t used = 0;
+            for (uint32_t v : rows) used += nchunks_of(rp[v + 1] - rp[v], ch);
+            for (uint64_t q = used; q < end; q++) { it[q] = Item{kNoVertex, 0, 0}; hb[q] = HubInfo{0, 1, 0, 0}; }
         }
         std::vector<uint32_t>().swap(mine[b]);
     }

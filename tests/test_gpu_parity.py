@@ -516,3 +516,33 @@ def test_checksum_detects_a_single_bit(cora):
         e.set_embeddings(Y)
         c = e.checksum()
     assert len({a, b, c}) == 3
+
+
+@pytest.mark.parametrize("model,bs", MODEL_CASES)
+@pytest.mark.parametrize("dim,batch,scale", [(128, 256, 12), (64, 37, 9), (128, 16, 10), (20, 100, 9), (256, 64, 10), (64, 1024, 13)])
+def test_dataflow_epoch_equals_launch_per_minibatch(oracle, model, bs, dim, batch, scale):
+    """Epoch mode 2 (ONE ordinary launch per epoch, no barrier: items handed out in order, a warp waits
+    only for the minibatches that wrote the rows it reads) is the same computation as mode 0 (one
+    launch per minibatch): bit-identical tables after 3 epochs, repeated to give races a chance, with
+    split hub rows, a partial last minibatch and batches small enough that dozens of dependent
+    minibatches are in flight at once -- and it agrees with the oracle."""
+    rp, ci = host.rmat_csr(scale, 16, 5)
+    n = len(rp) - 1
+    s = 5
+    full, neg = _streams(oracle, model, bs, rp, ci, dim, 3, batch, s)
+    out = []
+    for mode in (0, 2, 2, 2, 2):
+        with _engine(rp, ci, dim, full["X0"], model) as e:
+            e.set_epoch_mode(mode)
+            for it in range(3):
+                if model == 7:
+                    e.set_walks(full["walks"][it])
+                e.set_negatives(neg[it])
+                e.run_epoch(model, batch, s, bs, LR, chunk=32)
+            out.append(e.get_embeddings())
+            launches = e.launch_count()
+        if mode == 2:
+            assert launches == 3                 # one launch per epoch
+    for X in out[1:]:
+        assert np.array_equal(out[0], X)
+    np.testing.assert_allclose(out[0], full["X"], rtol=2e-4, atol=2e-5)
