@@ -1205,23 +1205,31 @@ force_flow_kernel(const FlowParams fp) {
     const BatchParams& p = fp.p;
     const int lane = threadIdx.x & 31;
     uint32_t rows_ok = 0;
+    constexpr uint32_t kTake = 4;            // lane-group rounds per ticket (one atomic per kTake * G items)
     for (;;) {
-        uint32_t t_base = 0;
-        if (lane == 0) t_base = atomicAdd(fp.ticket, (uint32_t)L::G);
-        t_base = __shfl_sync(kFull, t_base, 0);
-        if (t_base >= fp.total_items) break;
-        // minibatch of this warp's items: that of its first item (padding keeps a warp inside one minibatch;
-        // the first item of a group of kFlowPad is never a padding item)
-        const uint32_t v0 = p.items[t_base].v;
-        const uint32_t b = v0 / p.flow_batch;
-        BatchVar bv;
-        bv.items = p.items;
-        bv.hub = p.hub;
-        bv.n_items = fp.total_items;
-        bv.split = b * p.flow_batch;
-        bv.lo = bv.split;
-        bv.neg = p.neg + (size_t)b * fp.neg_stride;
-        process_items<L, MODEL, false>(p, bv, t_base, nullptr, nullptr, 0, lane, p.lut, 0u, rows_ok);
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(fp.ticket, kTake * (uint32_t)L::G);
+        t0 = __shfl_sync(kFull, t0, 0);
+        if (t0 >= fp.total_items) break;
+        // a warp works through its rounds in order, so everything it can wait for still belongs to items
+        // handed out earlier (to this warp or to others): the no-deadlock argument is unchanged
+        for (uint32_t r = 0; r < kTake; r++) {
+            const uint32_t t_base = t0 + r * (uint32_t)L::G;
+            if (t_base >= fp.total_items) break;
+            // minibatch of this round's items: that of the first one (padding keeps the lane groups of a
+            // round inside one minibatch; a round that starts with a padding item is all padding)
+            const uint32_t v0 = p.items[t_base].v;
+            if (v0 == kNoVertex) continue;
+            const uint32_t b = v0 / p.flow_batch;
+            BatchVar bv;
+            bv.items = p.items;
+            bv.hub = p.hub;
+            bv.n_items = fp.total_items;
+            bv.split = b * p.flow_batch;
+            bv.lo = bv.split;
+            bv.neg = p.neg + (size_t)b * fp.neg_stride;
+            process_items<L, MODEL, false>(p, bv, t_base, nullptr, nullptr, 0, lane, p.lut, 0u, rows_ok);
+        }
     }
 }
 

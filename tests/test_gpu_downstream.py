@@ -58,3 +58,21 @@ def test_option6_scores_match_oracle(cora, oracle):
     want = oracle.run(6, 0, rp, ci, 128, 1200, 256, 5, 0.02, threads=os.cpu_count() or 1)["X"]
     lp, nc = _compare(rp, ci, alg.nCoordinates, want)
     assert lp["accuracy"] > 0.95
+
+
+def test_option7_device_walk_sampler_scores_match_libc_walks(cora):
+    """`-walk 1` (the device sampler: counter-based draws, parallel) cannot consume the serial libc
+    stream, so its embeddings are not the reference's bit for bit -- its parity claim is downstream:
+    after the full reference configuration (cora, option 7, 1200 epochs) link-prediction accuracy / F1 /
+    AUC and node-classification F1 are within +-0.005 of the run that walks off the libc-compatible
+    stream (`-walk 0`, the path the reference-golden tests pin), same seeded splits."""
+    rp, ci = cora
+    runs = []
+    for walk in (0, 1):
+        alg = F.Algorithms(rp, ci, "cora.mtx", "/tmp/", 64)
+        alg.walk_sampler = walk
+        alg.AlgoForce2VecNSRWEFF(1200, 0, 256, 5, 0.02, write=False)
+        runs.append(alg.nCoordinates.copy())
+    assert not np.array_equal(runs[0], runs[1])               # different walks, different embeddings
+    lp, nc = _compare(rp, ci, runs[1], runs[0])
+    assert lp["accuracy"] > 0.9
