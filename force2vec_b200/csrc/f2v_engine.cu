@@ -209,8 +209,6 @@ struct Plan {
     std::vector<uint32_t> n_hub;            // hub-chunk items at the front of each minibatch
     Item* d_items = nullptr;
     HubInfo* d_hub = nullptr;
-    uint64_t* d_item_ptr = nullptr;         // nb+1 offsets (persistent epoch kernel)
-    uint64_t cap_ptr = 0;
     uint64_t cap_items = 0;
     uint32_t max_slots = 0;
 };
@@ -246,7 +244,6 @@ struct f2v_engine {
     int epoch_mode = 0;
     int variant = -1;                        // d=128 lane layout: -1 auto, see launch_batch
     int neg_smem = 1;
-    int epoch_ctas = 0;                      // persistent epoch kernel: CTAs per SM (0 = as many as fit)
     int auto_flow = 0;                       // epoch mode 0: batches up to this size run the dataflow epoch kernel (0 = never)
     bool flow_used = false;                  // a dataflow launch reports a wait time-out through d_done[1]
     uint32_t min_chunk = 0;                  // lower bound of the adaptive hub chunk (0 = default_min_chunk(batch))
@@ -263,7 +260,6 @@ struct f2v_engine {
     bool peer_ipc[kMaxWorld] = {};           // mapping opened with cudaIpcOpenMemHandle
     uint64_t* d_flags = nullptr;             // local flag page, kMaxWorld * kFlagStride u64
     uint32_t* d_done = nullptr;
-    uint32_t* d_bar = nullptr;               // grid-barrier counter of the persistent epoch kernel
     uint32_t* d_flow = nullptr;              // dataflow epoch: [ticket (128-byte line)] [cnt nb] [done nb]
     uint64_t flow_cap = 0;
     uint64_t step_id = 0;                    // minibatch steps published so far (same on every rank)
@@ -384,13 +380,6 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
         CU(cudaMemcpyAsync(pl.d_items, items.data(), sizeof(Item) * total, cudaMemcpyHostToDevice, e->stream));
         CU(cudaMemcpyAsync(pl.d_hub, hub.data(), sizeof(HubInfo) * total, cudaMemcpyHostToDevice, e->stream));
     }
-    if (pl.cap_ptr < nb + 1 || !pl.d_item_ptr) {
-        if (pl.d_item_ptr) CU(cudaFree(pl.d_item_ptr));
-        pl.d_item_ptr = nullptr; pl.cap_ptr = 0;
-        CU(cudaMalloc((void**)&pl.d_item_ptr, sizeof(uint64_t) * (nb + 1)));
-        pl.cap_ptr = nb + 1;
-    }
-    CU(cudaMemcpyAsync(pl.d_item_ptr, item_ptr.data(), sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice, e->stream));
     // on the engine's (non-blocking) stream, and finished before the host vectors go away: a copy on
     // the legacy stream would not be ordered before the launches that read the plan
     CU(cudaStreamSynchronize(e->stream));
@@ -482,7 +471,6 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         // option 7 2.42 -> 1.46 ms, option 6 1.41 -> 1.22 ms per epoch at batch 65536
         // (batch 16384, option 7: 2.82 / 1.90 / 2.09 ms for the three layouts; batch 4096: 5.76 / 6.72 / 7.03)
         switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u && model == kWalk ? 4 : (p.n_items >= 8000u ? 1 : 0))) {
-        case 20: return launch_batch_m<RingL<64, 8, 2, 5>>(model, p, st, sm_count);
         case 21: return launch_batch_m<RingL<64, 8, 3, 4>>(model, p, st, sm_count);
         case 22: return launch_batch_m<RingL<64, 8, 4, 3>>(model, p, st, sm_count);
         case 1: return launch_batch_m<VecL<64, 8, 2, 4>>(model, p, st, sm_count);
@@ -495,10 +483,8 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
         // slower below); small launches are latency-bound, not occupancy-bound, and run 8 rows in
         // flight per group at 128 registers (5-11 % faster below ~12 K items)
         switch (p.variant >= 0 ? p.variant : (p.n_items >= 48000u ? 8 : (p.n_items < 12000u ? 11 : 3))) {
-        case 20: return launch_batch_m<RingL<128, 16, 2, 5>>(model, p, st, sm_count);
         case 21: return launch_batch_m<RingL<128, 16, 3, 4>>(model, p, st, sm_count);
         case 22: return launch_batch_m<RingL<128, 16, 4, 3>>(model, p, st, sm_count);
-        case 23: return launch_batch_m<RingL<128, 16, 2, 4>>(model, p, st, sm_count);
         case 0: return launch_batch_m<VecL<128, 16, 4, 3>>(model, p, st, sm_count);
         case 8: return launch_batch_m<VecL<128, 16, 2, 5>>(model, p, st, sm_count);
         case 11: return launch_batch_m<VecL<128, 16, 8, 2>>(model, p, st, sm_count);
@@ -514,58 +500,6 @@ static cudaError_t launch_batch(int model, const BatchParams& p, cudaStream_t st
     if (p.dim <= 512) return launch_batch_m<GenL<16>>(model, p, st, sm_count);
     return launch_batch_m<GenL<32>>(model, p, st, sm_count);
 }
-
-// ---- persistent epoch kernel (epoch mode 1): cooperative launch, grid = SMs x resident CTAs
-template <class L, int MODEL>
-static cudaError_t launch_epoch_k(const EpochParams& ep, cudaStream_t st, int sm_count, int ctas_per_sm, unsigned* grid_out, bool query) {
-    auto kern = force_epoch_kernel<L, MODEL>;
-    const BatchParams& p = ep.p;
-    const bool negs = L::kBulk && p.neg_in_smem;
-    const bool lut_s = MODEL != kTDist && L::kBulk;
-    const size_t smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0) + (lut_s ? kLutAlloc * sizeof(float) : 0);
-    cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
-    const unsigned grid = (unsigned)(sm_count * per_sm);
-    *grid_out = grid;
-    if (query) return cudaSuccess;
-    void* args[] = {(void*)&ep};
-    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kWarpsPerCta * 32), args, smem, st);
-}
-
-template <class L>
-static cudaError_t launch_epoch_m(int model, const EpochParams& ep, cudaStream_t st, int sm_count, int cps, unsigned* grid, bool query) {
-    switch (model) {
-    case kTDist: return launch_epoch_k<L, kTDist>(ep, st, sm_count, cps, grid, query);
-    case kSigmoid: return launch_epoch_k<L, kSigmoid>(ep, st, sm_count, cps, grid, query);
-    default: return launch_epoch_k<L, kWalk>(ep, st, sm_count, cps, grid, query);
-    }
-}
-
-static cudaError_t launch_epoch(int model, const EpochParams& ep, cudaStream_t st, int sm_count, int cps, unsigned* grid, bool query) {
-    const uint32_t dim = ep.p.dim;
-    switch (dim) {
-    case 32: return launch_epoch_m<VecL<32, 8, 8>>(model, ep, st, sm_count, cps, grid, query);
-    case 64: return launch_epoch_m<VecL<64, 8, 4>>(model, ep, st, sm_count, cps, grid, query);
-    case 128: return launch_epoch_m<VecL<128, 16, 2, 4>>(model, ep, st, sm_count, cps, grid, query);
-    case 256: return launch_epoch_m<VecL<256, 32, 4>>(model, ep, st, sm_count, cps, grid, query);
-    default: break;
-    }
-    if (dim <= 32) return launch_epoch_m<GenL<1>>(model, ep, st, sm_count, cps, grid, query);
-    if (dim <= 64) return launch_epoch_m<GenL<2>>(model, ep, st, sm_count, cps, grid, query);
-    if (dim <= 128) return launch_epoch_m<GenL<4>>(model, ep, st, sm_count, cps, grid, query);
-    if (dim <= 256) return launch_epoch_m<GenL<8>>(model, ep, st, sm_count, cps, grid, query);
-    if (dim <= 512) return launch_epoch_m<GenL<16>>(model, ep, st, sm_count, cps, grid, query);
-    return launch_epoch_m<GenL<32>>(model, ep, st, sm_count, cps, grid, query);
-}
-
 
 // ---- dataflow epoch kernel (epoch mode 2): ordinary launch, grid = SMs x resident CTAs
 template <class L, int MODEL>
@@ -590,17 +524,14 @@ static cudaError_t launch_flow_m(int model, const FlowParams& fp, cudaStream_t s
     }
 }
 static cudaError_t launch_flow(int model, const FlowParams& fp, cudaStream_t st, int sm_count, int variant) {
+    // (with many minibatches in flight a warp's latency matters more than occupancy: the layouts with the
+    // most rows in flight per lane group measured fastest here -- d=128: 8 rows at 128 registers)
+    (void)variant;
     const uint32_t dim = fp.p.dim;
     switch (dim) {
     case 32: return launch_flow_m<VecL<32, 8, 8>>(model, fp, st, sm_count);
-    case 64: return variant == 0 ? launch_flow_m<VecL<64, 8, 4>>(model, fp, st, sm_count)
-                                 : launch_flow_m<VecL<64, 8, 2, 4>>(model, fp, st, sm_count);
-    case 128:
-        switch (variant) {
-        case 8: return launch_flow_m<VecL<128, 16, 2, 5>>(model, fp, st, sm_count);
-        case 11: return launch_flow_m<VecL<128, 16, 8, 2>>(model, fp, st, sm_count);
-        default: return launch_flow_m<VecL<128, 16, 2, 4>>(model, fp, st, sm_count);
-        }
+    case 64: return launch_flow_m<VecL<64, 8, 4>>(model, fp, st, sm_count);
+    case 128: return launch_flow_m<VecL<128, 16, 8, 2>>(model, fp, st, sm_count);
     case 256: return launch_flow_m<VecL<256, 32, 4>>(model, fp, st, sm_count);
     default: break;
     }
@@ -796,9 +727,8 @@ int f2v_destroy(f2v_engine* e) {
     cudaFree(e->d_rowptr); cudaFree(e->d_colids); cudaFree(e->d_Xall);
     cudaFree(e->d_lut); cudaFree(e->d_neg); cudaFree(e->d_walks); cudaFree(e->d_stage);
     cudaFree(e->d_partials); cudaFree(e->d_counters);
-    cudaFree(e->epoch_plan.d_items); cudaFree(e->epoch_plan.d_hub); cudaFree(e->epoch_plan.d_item_ptr);
-    cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub); cudaFree(e->step_plan.d_item_ptr);
-    cudaFree(e->d_bar);
+    cudaFree(e->epoch_plan.d_items); cudaFree(e->epoch_plan.d_hub);
+    cudaFree(e->step_plan.d_items); cudaFree(e->step_plan.d_hub);
     cudaFree(e->d_flow);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1085,7 +1015,6 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     }
     r = ensure_tables(e);
     if (r) return r;
-    if (e->shard_mode && e->epoch_mode != 0) return fail(F2V_ERR_STATE, "row-sharded engines run epoch mode 0");
     const int order = e->order >= 0 ? e->order : (e->peer_mode ? 1 : 0);
     // dataflow epoch (mode 2, or mode 0 = automatic at small batches): single-GPU engines, at least two minibatches
     const bool flow = e->world == 1 && nb >= 2 && nb * (uint64_t)batch < 0xffffffffull &&
@@ -1162,31 +1091,6 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
         e->cur = 1 - e->cur;
         return F2V_OK;
     }
-    if (e->epoch_mode == 1 && nb >= 1 && !(e->world > 1 && !e->peer_mode)) {
-        // one persistent cooperative launch for the whole epoch
-        EpochParams ep{};
-        ep.p = p;
-        ep.p.items = pl.d_items; ep.p.hub = pl.d_hub; ep.p.neg = e->d_neg + e->neg_off;
-        ep.p.pdl = 0; ep.p.wait_step = 0; ep.p.signal_step = 0;
-        ep.item_ptr = pl.d_item_ptr; ep.nb = (uint32_t)nb; ep.batch = batch; ep.neg_stride = (uint32_t)W;
-        ep.step0 = e->step_id;
-        unsigned grid = 0;
-        CU(launch_epoch(model, ep, e->stream, e->sm_count, e->epoch_ctas, &grid, true));
-        if ((uint64_t)grid * nb < 0xffffffffull) {
-            if (!e->d_bar) CU(cudaMalloc((void**)&e->d_bar, 128));
-            CU(cudaMemsetAsync(e->d_bar, 0, 128, e->stream));
-            ep.bar_count = e->d_bar;
-            CU(launch_epoch(model, ep, e->stream, e->sm_count, e->epoch_ctas, &grid, false));
-            e->launches++;
-            if (e->peer_mode) e->step_id += nb;
-            if (X_out_host)
-                CU(cudaMemcpyAsync(X_out_host, Xnew, sizeof(float) * e->n * e->dim, cudaMemcpyDeviceToHost, e->stream));
-            CU(cudaEventRecord(e->ev1, e->stream));
-            e->ev_valid = true;
-            e->cur = 1 - e->cur;
-            return F2V_OK;
-        }
-    }
     uint64_t copy_lo = 0;
     if (e->trace) {
         while (e->trace_ev.size() < nb + 1) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->trace_ev.push_back(ev); }
@@ -1223,6 +1127,7 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
             p.signal_step = 0;
             p.late_wait = p.pdl != 0;        // the first (ordinary) launch waits at kernel entry: its own rows of the
                                              // current table may just have been uploaded / broadcast by a peer
+            p.flow_batch = batch;            // (row -> exchange step mapping of the lazy wait)
             if (p.n_items) {
                 CU(launch_batch(model, p, e->stream, e->sm_count));
                 e->launches++;
@@ -1358,7 +1263,9 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
 
 int f2v_set_epoch_mode(f2v_engine* e, int mode) {
     if (!e) return fail(F2V_ERR_ARG, "null engine");
-    if (mode != 0 && mode != 1 && mode != 2) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
+    if (mode == 1) return fail(F2V_ERR_ARG, "epoch mode 1 (persistent kernel with a grid barrier per minibatch) was removed: "
+                                            "it lost to mode 0 at every batch size; mode 2 is the one-launch-per-epoch mode");
+    if (mode != 0 && mode != 2) return fail(F2V_ERR_ARG, "epoch mode %d not available", mode);
     e->epoch_mode = mode;
     return F2V_OK;
 }
@@ -1376,7 +1283,6 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "trace")) e->trace = (int)value;
     else if (!strcmp(name, "exchange_timeout_ms")) e->exchange_timeout_ms = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "sharded")) e->want_shard = value != 0;
-    else if (!strcmp(name, "epoch_ctas")) e->epoch_ctas = (int)value;
     else if (!strcmp(name, "auto_flow")) e->auto_flow = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "min_chunk")) e->min_chunk = (uint32_t)std::max<int64_t>(0, value);   // part of the plan cache key
     else return fail(F2V_ERR_ARG, "unknown option %s", name);

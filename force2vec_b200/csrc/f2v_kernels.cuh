@@ -22,9 +22,13 @@
 #include <stdint.h>
 #include "f2v_plan.hpp"
 
-// How gathered embedding rows are loaded: __ldcg (L2 only), __ldca (L1 + L2) or __ldg
-// (non-coherent path).  Every row a launch gathers is read-only for that launch (it writes only
-// rows of its own minibatch into the next table, which it never reads), so all three are legal.
+// How gathered embedding rows (and an item's own row) are loaded: __ldcg (L2 only, default) or
+// __ldca (L1 + L2: hub rows that most vertices gather then hit in the SM's own L1 instead of all
+// converging on the few L2 slices that hold them).  L1 is legal for them: within an epoch a launch
+// reads next-table rows only below its split (final since an earlier minibatch, never cached before
+// they were final) and current-table rows (nobody writes them during the epoch), and the epoch's
+// first launch is an ordinary launch that starts from an invalidated L1.  It is NOT legal for the
+// hub partial sums other CTAs store during the same launch: fold_rows() always loads with __ldcg.
 #ifndef F2V_ROW_LOAD
 #define F2V_ROW_LOAD __ldcg
 #endif
@@ -150,19 +154,6 @@ __device__ __forceinline__ uint32_t table_row(const BatchParams& p, uint32_t j, 
     return shard_row(j, p.shard_lg, p.shard_rows) + (j < split ? p.off_lo : p.off_hi);
 }
 
-// One persistent launch per epoch (f2v_set_epoch_mode 1): every CTA loops over the minibatches,
-// separated by a grid barrier.  p.items / p.hub / p.neg are the bases of the epoch's plan and
-// negative stream.
-struct EpochParams {
-    BatchParams p;
-    const uint64_t* item_ptr;   // nb + 1 offsets into items / hub (device)
-    uint32_t nb;
-    uint32_t batch;
-    uint32_t neg_stride;        // negative indices per minibatch
-    uint32_t* bar_count;        // grid-barrier arrival counter, zeroed before the launch
-    uint64_t step0;             // multi-GPU: exchange step published before this epoch's first minibatch
-};
-
 // ------------------------------------------------------------------ PTX helpers --------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -282,6 +273,14 @@ struct VecL {
             f[4 * k + 0] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
         }
     }
+    // L2-only load: data other CTAs of the same launch may have written (hub partial sums)
+    __device__ static __forceinline__ void load_cg(float (&f)[NE], const float* row, int l, uint32_t) {
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            float4 t = __ldcg(reinterpret_cast<const float4*>(row) + k * LPR + l);
+            f[4 * k + 0] = t.x; f[4 * k + 1] = t.y; f[4 * k + 2] = t.z; f[4 * k + 3] = t.w;
+        }
+    }
     __device__ static __forceinline__ void load_s(float (&f)[NE], const float* row, int l, uint32_t) {
 #pragma unroll
         for (int k = 0; k < VPL; k++) {
@@ -398,6 +397,7 @@ struct GenL {
             f[k] = e < dim ? __ldcg(row + e) : 0.f;
         }
     }
+    __device__ static __forceinline__ void load_cg(float (&f)[NE], const float* row, int l, uint32_t dim) { load_g(f, row, l, dim); }
     __device__ static __forceinline__ void load_s(float (&f)[NE], const float* row, int l, uint32_t dim) {
 #pragma unroll
         for (int k = 0; k < NV; k++) {
@@ -601,6 +601,45 @@ __device__ __forceinline__ void flow_wait(const BatchParams& p, uint32_t need, u
     rows_ok = max(rows_ok, min(F * p.flow_batch, p.flow_n));
 }
 
+// Multi-GPU, PDL-chained launches: the LAZY exchange wait.  Minibatch b's launch may only read a row
+// of the next table written by a PEER once that peer has published the step of the row's minibatch --
+// but most rows a warp gathers were written many minibatches ago, and only a fraction of the items
+// touch the previous minibatch at all.  So instead of every warp waiting for every peer's previous
+// step before it reads anything, a warp looks at the ids it is about to gather: `need` = 1 + the
+// largest vertex id below the split (0 = none).  Rows [0, rows_ok) are known to be complete in every
+// replica (per-warp register); if need exceeds it the lanes read the peers' step counters (relaxed
+// loads, local memory) and derive how far back the slowest peer is: step wait_step covers rows below
+// the split, each step before it one minibatch less.  Only a warp whose rows are really not there yet
+// spins.  The exchange latency and the ranks' imbalance then hide behind the items that do not depend
+// on the previous minibatch, instead of idling the whole GPU once per minibatch.
+__device__ __forceinline__ void lazy_peer_wait(const BatchParams& p, uint32_t need, uint32_t split, uint32_t& rows_ok, int lane) {
+    if (need <= rows_ok) return;
+    const bool poll = (uint32_t)lane < p.world && ((uint32_t)lane != p.rank || p.mc_flag != nullptr);
+    const uint64_t* f = p.flags + (size_t)lane * kFlagStride;
+    uint64_t t0 = 0;
+    uint32_t ok = rows_ok;
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t lag = 0;                                  // minibatches this peer is behind wait_step
+        if (poll) {
+            const uint64_t v = ld_relaxed_sys(f);
+            lag = v >= p.wait_step ? 0u : (uint32_t)min(p.wait_step - v, (uint64_t)0xffffffu);
+        }
+        lag = __reduce_max_sync(kFull, lag);
+        const uint64_t behind = (uint64_t)lag * p.flow_batch;
+        ok = behind >= split ? 0u : split - (uint32_t)behind;
+        if (need <= ok) break;
+        if ((spins & 7u) == 7u) __nanosleep(64);
+        if ((spins & 255u) == 255u && p.timeout_ns) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > p.timeout_ns) { if (p.timed_out && lane == 0) atomicExch(p.timed_out, 1u); break; }
+        }
+    }
+    if (poll) (void)ld_acquire_sys(f);                     // order the row reads that follow
+    __syncwarp();
+    rows_ok = max(rows_ok, ok);
+}
+
 // Every group gathers its own `cnt` rows named by idx[0..cnt) (in order) and folds them into
 // its acc.  Indices are fetched LPR at a time per group (coalesced) and broadcast inside the
 // group by shuffle; U row loads per group (G*U per warp) are in flight.
@@ -622,6 +661,8 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
         uint32_t mine = (have_first && base == 0) ? first : ((uint32_t)l < nb ? __ldcg(idx + base + l) : self);
         if (p.flow_done != nullptr)                      // dataflow epoch: the writers of the rows below the split must be done
             flow_wait(p, __reduce_max_sync(kFull, mine < split ? mine + 1u : 0u), rows_ok, (int)(threadIdx.x & 31));
+        else if (p.late_wait)                            // multi-GPU: the peers that wrote them must have published their step
+            lazy_peer_wait(p, __reduce_max_sync(kFull, mine < split ? mine + 1u : 0u), split, rows_ok, (int)(threadIdx.x & 31));
         mine = table_row(p, mine, split);                // row of the combined table
         for (uint32_t t0 = 0; t0 < nb_max; t0 += U) {
             float rows[U][L::NE];
@@ -727,10 +768,14 @@ __device__ __forceinline__ void gather_stream(float (&acc)[L::NE], const float (
         else if (P < cnt) j = __ldcg(idxB + (P - cntA));
         if (p.flow_done != nullptr)
             flow_wait(p, __reduce_max_sync(kFull, j < split ? j + 1u : 0u), rows_ok, (int)(threadIdx.x & 31));
+        else if (p.late_wait)
+            lazy_peer_wait(p, __reduce_max_sync(kFull, j < split ? j + 1u : 0u), split, rows_ok, (int)(threadIdx.x & 31));
         return table_row(p, j, split);
     };
     if (have_first && p.flow_done != nullptr)
         flow_wait(p, __reduce_max_sync(kFull, first < split ? first + 1u : 0u), rows_ok, (int)(threadIdx.x & 31));
+    else if (have_first && p.late_wait)
+        lazy_peer_wait(p, __reduce_max_sync(kFull, first < split ? first + 1u : 0u), split, rows_ok, (int)(threadIdx.x & 31));
     uint32_t ids_cur = have_first ? table_row(p, first, split) : load_ids(0);   // block of the copy pointer
     uint32_t ids_nxt = cnt_max > (uint32_t)LPR ? load_ids(LPR) : 0u;             // the block after it
     uint32_t blk = 0;                                                            // block index of ids_cur
@@ -789,7 +834,7 @@ __device__ __forceinline__ void fold_rows(float (&acc)[L::NE], const float* rows
     for (; c + CU <= cnt; c += CU) {
         float part[CU][NE];
 #pragma unroll
-        for (int u = 0; u < CU; u++) L::load_g(part[u], rows + (size_t)(c + u) * rs, l, dim);
+        for (int u = 0; u < CU; u++) L::load_cg(part[u], rows + (size_t)(c + u) * rs, l, dim);
 #pragma unroll
         for (int u = 0; u < CU; u++)
 #pragma unroll
@@ -797,7 +842,7 @@ __device__ __forceinline__ void fold_rows(float (&acc)[L::NE], const float* rows
     }
     for (; c < cnt; c++) {
         float part[NE];
-        L::load_g(part, rows + (size_t)c * rs, l, dim);
+        L::load_cg(part, rows + (size_t)c * rs, l, dim);
 #pragma unroll
         for (int k = 0; k < NE; k++) acc[k] += part[k];
     }
@@ -870,7 +915,7 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     // (The item's own row comes from the current table, which nobody writes between the epoch's first
     // launch -- an ordinary launch that waits at kernel entry, because an upload / broadcast may just
     // have rewritten the current table -- and the epoch's end.)
-    if (p.late_wait) peer_wait_warp(p, lane);
+    // -> the wait itself is lazy: lazy_peer_wait() in the gather, on the ids about to be read
     float sd = 0.f;
     if (MODEL != kTDist) {
         // degi = 1.0/(deg+1) stored to float (algorithms.cpp:852,1159); STEP*degi in float
@@ -1055,7 +1100,15 @@ force_batch_kernel(const BatchParams p) {
             const uint32_t lut_bytes = LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u;
             if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes + lut_bytes);
             if (p.pdl) pdl_wait();                  // negative rows may have been written by the previous minibatch
-            if (p.late_wait) { publish_predecessor(p); peer_wait_warp(p, (int)threadIdx.x); }
+            if (p.late_wait) {
+                publish_predecessor(p);
+                uint32_t need = 0, ro = 0;                 // the staged negative rows that lie below the split
+                for (uint32_t q = threadIdx.x; negs && q < p.s; q += 32) {
+                    const uint32_t jn = __ldcg(bv.neg + q);
+                    if (jn < bv.split) need = max(need, jn + 1u);
+                }
+                lazy_peer_wait(p, __reduce_max_sync(kFull, need), bv.split, ro, (int)threadIdx.x);
+            }
             if (p.wait_step || p.pdl) fence_proxy_async();   // rows written with generic stores (here or by peers) are read by TMA next
             __syncwarp();
             if (negs) stage_negatives<L>(p, bv, s_neg, bar);
@@ -1088,100 +1141,6 @@ force_batch_kernel(const BatchParams p) {
     if (negs || LS) mbar_wait(bar, 0);
     peer_signal(p);
 }
-
-// ------------------------------------------------------------------ persistent epoch ---
-__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Grid barrier between two minibatches of the persistent epoch kernel: every row stored by this
-// CTA is visible to the whole grid (and, on a multi-GPU engine, performed in the peers' replicas:
-// system-scope fence) before any CTA reads it.  The last CTA to arrive publishes the exchange step
-// to the peers.  `target` = arrivals expected so far (monotone counter, zeroed before the launch).
-__device__ __forceinline__ void grid_barrier(const BatchParams& p, uint32_t* counter, uint32_t target, uint64_t step) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (p.n_peers) __threadfence_system(); else __threadfence();
-        const uint32_t old = atomicAdd(counter, 1u);
-        if (p.n_peers && old == target - 1) {
-            __threadfence_system();
-            publish_step(p, step);
-        }
-        while (ld_acquire_gpu_u32(counter) < target) {}
-    }
-    if (p.n_peers && threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
-        const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
-        wait_flag(f, step, p.timeout_ns, p.timed_out);
-    }
-    __syncthreads();
-}
-
-// The whole epoch in one cooperative launch: grid = SMs x resident CTAs; per minibatch every warp
-// strides over the item list (longest items first), the CTA re-stages the minibatch's shared
-// negative rows by TMA, and a grid barrier separates consecutive minibatches (Jacobi rule:
-// minibatch b+1 reads rows minibatch b wrote).  The sigmoid table lives in shared memory for the
-// whole epoch.  For small minibatches this replaces a launch + drain per minibatch (~10 us) by a
-// barrier (~1-2 us).
-template <class L, int MODEL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, L::MINB)
-force_epoch_kernel(const EpochParams ep) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const BatchParams& p = ep.p;
-    constexpr bool LS = MODEL != kTDist && L::kBulk;
-    uint64_t* bar_neg = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* bar_lut = bar_neg + 1;
-    const bool negs = L::kBulk && p.neg_in_smem;
-    float* s_neg = negs ? reinterpret_cast<float*>(smem_raw + 128) : nullptr;
-    const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
-    const float* lut = p.lut;
-    if (threadIdx.x == 0) { mbar_init(bar_neg, 1); mbar_init(bar_lut, 1); fence_mbar_init(); }
-    __syncthreads();
-    if (LS) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar_lut, (uint32_t)(kLutAlloc * sizeof(float)));
-            bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, (uint32_t)(kLutAlloc * sizeof(float)), bar_lut);
-        }
-        lut = reinterpret_cast<const float*>(smem_raw + 128 + neg_bytes);
-        mbar_wait(bar_lut, 0);
-    }
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
-    uint32_t rows_ok = 0;
-    if (p.n_peers && ep.step0) {
-        // rows the peers stored during the previous epoch's last minibatch
-        if (threadIdx.x < p.world && (threadIdx.x != p.rank || p.mc_flag != nullptr)) {
-            const uint64_t* f = p.flags + (size_t)threadIdx.x * kFlagStride;
-            wait_flag(f, ep.step0, p.timeout_ns, p.timed_out);
-        }
-        __syncthreads();
-    }
-    for (uint32_t b = 0; b < ep.nb; b++) {
-        const uint64_t i0 = ep.item_ptr[b], i1 = ep.item_ptr[b + 1];
-        BatchVar bv;
-        bv.items = p.items + i0;
-        bv.hub = p.hub + i0;
-        bv.n_items = (uint32_t)(i1 - i0);
-        bv.split = b * ep.batch;
-        bv.lo = b * ep.batch;
-        bv.neg = p.neg + (size_t)b * ep.neg_stride;
-        if (negs && threadIdx.x < 32) {
-            if (threadIdx.x == 0) mbar_expect_tx(bar_neg, neg_bytes);
-            fence_proxy_async();        // rows written with generic stores (this GPU or a peer) are read by TMA next
-            __syncwarp();
-            stage_negatives<L>(p, bv, s_neg, bar_neg);
-        }
-        for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
-            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar_neg, b & 1u, lane, lut, 0u, rows_ok);
-        // the staged rows must have landed before shared memory is reused / the CTA exits
-        if (negs) mbar_wait(bar_neg, b & 1u);
-        if (b + 1 < ep.nb || p.n_peers)
-            grid_barrier(p, ep.bar_count, (b + 1) * gridDim.x, ep.step0 + b + 1);
-    }
-}
-
 
 // ------------------------------------------------------------------ dataflow epoch kernel
 // The whole epoch in ONE ordinary launch with no barrier at all (f2v_set_epoch_mode 2).  The epoch's

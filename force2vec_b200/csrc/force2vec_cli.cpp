@@ -35,7 +35,7 @@ static void helpmessage() {
     printf("        -option 7 - for sigmoid + semi-random walk (rForce2Vec).\n");
     printf("-device <int>, (first) CUDA device. (default:0)\n");
     printf("-gpus <int>, number of GPUs; minibatches are split across them. (default:1)\n");
-    printf("-mode <int>, 0 = one launch per minibatch, 1 = persistent epoch kernel. (default:0)\n");
+    printf("-mode <int>, 0 = one launch per minibatch, 2 = one dataflow launch per epoch. (default:0)\n");
     printf("-walk <int>, option 7 walks: 0 = host (reference stream), 1 = device sampler. (default:0)\n");
     printf("-h, show help message.\n");
 }

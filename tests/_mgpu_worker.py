@@ -46,12 +46,12 @@ def main():
         # peer: NVLink multicast stores where the box supports them; peer_unicast: one store per peer
         # peer_fallback: rank 0 reports that the multicast object cannot be created -> all ranks go unicast
         # peer_sharded: row-sharded tables (each GPU stores 1/world of the rows, gathers cross NVLink)
-        for comm in ("peer", "peer_unicast", "peer_fallback", "peer_persistent", "peer_sharded", "nccl"):
+        for comm in ("peer", "peer_unicast", "peer_fallback", "peer_nopdl", "peer_sharded", "nccl"):
             if comm == "peer_sharded" and world & (world - 1):
                 continue
             multi = F.Engine(rp, ci, dim, device=local)
-            if comm == "peer_persistent":
-                multi.set_epoch_mode(1)          # one cooperative launch per epoch, exchange barrier inside
+            if comm == "peer_nopdl":
+                multi.set_option("pdl", 0)       # ordinary launches: every launch waits for the peers at kernel entry
             if comm == "peer_unicast":
                 multi.set_option("multicast", 0)
             if comm == "peer_fallback":
