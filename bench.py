@@ -40,7 +40,7 @@ MODEL_NAMES = {5: "tForce2Vec", 6: "sForce2Vec", 7: "rForce2Vec"}
 WORKLOADS = {
     "cfg2": dict(scale=20, model=6, dim=128, bs=0, batch=65536),
     "cfg3": dict(scale=22, model=7, dim=64, bs=0, batch=65536),
-    "cfg4": dict(scale=24, model=5, dim=128, bs=1, batch=65536),
+    "cfg4": dict(scale=24, model=5, dim=128, bs=1, batch=262144),
     "cfg5": dict(scale=26, model=5, dim=128, bs=0, batch=262144),
 }
 
@@ -67,7 +67,9 @@ def parse():
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N>1 exchange: peer = stores into the peers' replicas fused into the force kernel; "
                          "nccl = all-gather per minibatch (baseline)")
-    ap.add_argument("--multicast", type=int, default=1, help="peer exchange through NVLink multicast (NVLS) stores")
+    ap.add_argument("--multicast", type=int, default=1,
+                    help="peer exchange through NVLink multicast (NVLS) stores: 1 = from three ranks on (two ranks: one store "
+                         "per peer is as cheap and skips the loop through the switch), 0 = never, 3 = always")
     ap.add_argument("--sharded", type=int, default=0, help="N>1: row-sharded tables instead of replicas (capacity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -307,10 +309,10 @@ def make_engine(F, a, rp, ci, local, stream=None):
     return eng
 
 
-def checked_epoch(F, a, rp, ci, local, X0, neg0, multi, dist, torch, rank, world):
-    """N > 1: one epoch from the same state on a single-GPU engine (this rank's device) and on the
-    N-rank engine, same hub chunk length: every replica must equal the single-GPU table bit for bit
-    (device checksum over the whole table + probe rows compared value by value)."""
+def checked_epoch_single(F, a, rp, ci, local, X0, neg0):
+    """N > 1, first half of the checked epoch: one epoch from the initial state on a SINGLE-GPU engine on
+    this rank's device (created, run and destroyed before the N-rank engine exists: at scale 26 the two
+    would not fit one GPU together).  Returns what the N-rank result is compared with."""
     chunk = a.chunk or 64
     n = len(rp) - 1
     probe = sorted(set(int(x) for x in np.linspace(0, n - 1, 64)))
@@ -322,20 +324,29 @@ def checked_epoch(F, a, rp, ci, local, X0, neg0, multi, dist, torch, rank, world
     single.run_epoch(a.model, a.batch, a.nsamples, a.bs, a.lr, chunk)
     h1 = single.checksum()
     rows1 = np.stack([single.get_rows(v, 1)[0] for v in probe])
+    ms = single.last_epoch_ms()
     single.close()
+    return {"chunk": chunk, "probe": probe, "checksum": h1, "rows": rows1, "epoch_ms": ms}
+
+
+def checked_epoch_multi(a, ref, X0, neg0, multi, dist, torch):
+    """Second half: the same epoch on the N-rank engine, same hub chunk length: every replica (or the
+    row-sharded table) must equal the single-GPU table bit for bit -- device checksum over the whole
+    table + probe rows compared value by value, on every rank."""
     multi.set_embeddings(X0)
     multi.set_negatives(neg0)
     if a.model == 7:
         multi.sample_walks(1, 0)
-    multi.run_epoch(a.model, a.batch, a.nsamples, a.bs, a.lr, chunk)
+    multi.run_epoch(a.model, a.batch, a.nsamples, a.bs, a.lr, ref["chunk"])
     hN = multi.checksum()
-    rowsN = np.stack([multi.get_rows(v, 1)[0] for v in probe])
-    same = (h1 == hN) and np.array_equal(rows1, rowsN)
+    rowsN = np.stack([multi.get_rows(v, 1)[0] for v in ref["probe"]])
+    same = (ref["checksum"] == hN) and np.array_equal(ref["rows"], rowsN)
     t = torch.tensor([1 if same else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    return {"vs": "single_gpu", "bit_exact": bool(int(t.item()) == 1), "checksum": "%016x" % h1,
-            "checksum_this_rank": "%016x" % hN, "epochs": 1, "chunk": chunk, "probe_rows": len(probe),
-            "checked_on": "every rank's replica against a single-GPU engine on the same device"}
+    return {"vs": "single_gpu", "bit_exact": bool(int(t.item()) == 1), "checksum": "%016x" % ref["checksum"],
+            "checksum_this_rank": "%016x" % hN, "epochs": 1, "chunk": ref["chunk"], "probe_rows": len(ref["probe"]),
+            "single_gpu_epoch_ms": ref["epoch_ms"],
+            "checked_on": "every rank's table against a single-GPU engine run on the same device"}
 
 
 def run_ours(a):
@@ -387,6 +398,10 @@ def run_ours(a):
         if rank != 0:
             neg_np[:] = np.load(path, mmap_mode="r")
 
+    parity_ref = None
+    if world > 1 and not a.no_parity:
+        parity_ref = checked_epoch_single(F, a, rp, ci, local, X0, neg_np[:stride])
+
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -405,8 +420,8 @@ def run_ours(a):
         eng.comm_peer_init(blobs, rank, world)
 
     parity = None
-    if world > 1 and not a.no_parity:
-        parity = checked_epoch(F, a, rp, ci, local, X0, neg_np[:stride], eng, dist, torch, rank, world)
+    if parity_ref is not None:
+        parity = checked_epoch_multi(a, parity_ref, X0, neg_np[:stride], eng, dist, torch)
         if not parity["bit_exact"]:
             if rank == 0:
                 print(json.dumps({"error": "multi-GPU table differs from the single-GPU run", "parity": parity}), flush=True)

@@ -266,6 +266,8 @@ struct f2v_engine {
     // NVLink multicast (NVLS) exchange: tables + flag page live in one VMM allocation bound to a
     // multicast object shared by all ranks; a store through the multicast mapping lands everywhere
     int want_mc = 1;                         // option "multicast": use NVLS when every rank supports it
+    int mc_inproc = 0;                       // option "multicast_in_process": the caller drives every engine of this process
+                                             // from its own host thread, so the (blocking) hand-off may run between them
     bool mc_mode = false;
     CUmemGenericAllocationHandle mc_handle = 0, vmm_handle = 0;
     CUdeviceptr vmm_uc = 0, vmm_mc = 0;
@@ -998,9 +1000,11 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     if (e->world > 1 && !e->peer_mode && batch % e->world)
         return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
     CU(cudaSetDevice(e->device));
-    // default hub chunk: 128 edges on one GPU; 64 on a multi-GPU engine, where a rank's share of a
-    // minibatch is small enough for the longest item to be the critical path (measured, N=4)
-    if (chunk == 0) chunk = e->world > 1 ? 64 : 128;
+    // default hub chunk: 128 edges; 64 on a multi-GPU engine whose share of a minibatch is small enough
+    // (< 16 K rows per rank) for the longest item to be the critical path (measured at N=4 on R-MAT 20;
+    // with large shares shorter chunks only add partial-sum traffic: R-MAT 24, N=2, 256 K rows per
+    // minibatch: 24.6 ms per epoch at 128, 26.9 at 64, 29.1 at 32 -- profiles/r2_mgpu_cfg4.md)
+    if (chunk == 0) chunk = (e->world > 1 && batch / (uint32_t)e->world < 16384u) ? 64 : 128;
     const uint64_t nb = (e->n + batch - 1) / batch;
     const uint64_t W = neg_stride(model, batch, s, bs_mode);
     if (e->neg_count < e->neg_off + nb * W)
@@ -1280,6 +1284,7 @@ int f2v_set_option(f2v_engine* e, const char* name, int64_t value) {
     else if (!strcmp(name, "pdl")) e->pdl = (int)value;
     else if (!strcmp(name, "order")) e->order = (int)value;
     else if (!strcmp(name, "multicast")) e->want_mc = (int)value;
+    else if (!strcmp(name, "multicast_in_process")) e->mc_inproc = value != 0;
     else if (!strcmp(name, "trace")) e->trace = (int)value;
     else if (!strcmp(name, "exchange_timeout_ms")) e->exchange_timeout_ms = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "sharded")) e->want_shard = value != 0;
@@ -1384,7 +1389,7 @@ int f2v_comm_peer_export(f2v_engine* e, void* blob) {
                 else if (s >= 0) close(s);
             }
             if (e->listen_sock >= 0) {
-                b.mc_ok = 1;
+                b.mc_ok = 1u | (e->mc_inproc ? 2u : 0u) | (e->want_mc == 3 ? 4u : 0u);
                 memcpy(b.sock_name, e->sock_name, std::min(sizeof(b.sock_name) - 1, strlen(e->sock_name)));
             }
         }
@@ -1714,7 +1719,8 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
             if (all[r].cur != (uint64_t)e->cur) return fail(F2V_ERR_STATE, "rank %d is at a different table parity", r);
             mc = mc && all[r].mc_ok != 0;
             nshard += all[r].shard != 0;
-            for (int q = 0; q < r; q++) mc = mc && all[q].pid != all[r].pid;
+            // engines of ONE process: only if the caller promised a host thread per engine (the hand-off blocks)
+            for (int q = 0; q < r; q++) mc = mc && (all[q].pid != all[r].pid || ((all[q].mc_ok & 2u) && (all[r].mc_ok & 2u)));
         }
         if (nshard != 0 && nshard != world) return fail(F2V_ERR_ARG, "the option \"sharded\" must be set on every rank or on none");
         if (nshard) {
@@ -1724,6 +1730,12 @@ int f2v_comm_peer_init(f2v_engine* e, const void* blobs, int rank, int world) {
             if (rr) return rr;
             mc = false;                        // rows are stored once, in their shard: nothing to multicast
         }
+        // two ranks: one store per peer is the same NVLink egress as a multicast store, and the rank's own copy
+        // does not loop through the switch (measured, R-MAT 24 option 5: 22.4 vs 24.5 ms per epoch); from
+        // three ranks on multicast wins (egress 1x instead of (N-1)x).  "multicast" = 3 forces it at N=2.
+        bool forced = true;                                        // (every rank must take the same decision: it is
+        for (int r = 0; r < world; r++) forced = forced && (all[r].mc_ok & 4u);   // derived from the exchanged blobs only)
+        if (mc && world == 2 && !forced) mc = false;
         if (mc) {
             int rr = mc_setup(e, all, rank, world);
             if (rr) return rr;

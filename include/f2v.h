@@ -122,9 +122,9 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows,
  * ranges in natural order (algorithms.cpp:569-640), consuming the resident negative
  * stream (ceil(n/batch)*W entries) and, for model 7, the resident walks.  Same result
  * as a loop of f2v_step.  Asynchronous on the engine's stream.
- * chunk: hub rows longer than `chunk` edges are split across warps (0 = default: 128 on a
- * single-GPU engine, 64 on a multi-GPU one).  Results are bit-identical across world sizes
- * and epoch modes for equal `chunk`.                                                   */
+ * chunk: hub rows longer than `chunk` edges are split across warps (0 = default: 128; 64 on a
+ * multi-GPU engine whose share of a minibatch is below 16 K rows).  Results are bit-identical
+ * across world sizes and epoch modes for equal `chunk`.                                */
 int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode,
                   float lr, uint32_t chunk);
 
@@ -140,26 +140,36 @@ int f2v_run_epoch_host(f2v_engine* e, int model, uint32_t batch, uint32_t s, int
                        const uint32_t* neg_idx_host, uint64_t neg_count,
                        const uint32_t* walks_host, float* X_out);
 
-/* Execution mode of f2v_run_epoch: 0 = one kernel launch per minibatch (default),
- * 1 = one persistent cooperative kernel per epoch with a grid barrier per minibatch.  */
+/* Execution mode of f2v_run_epoch: 0 = one kernel launch per minibatch, chained by programmatic
+ * dependent launch (default); 2 = the dataflow epoch: ONE ordinary launch per epoch, items handed out
+ * in order, a warp waits only for the minibatches that wrote the rows it is about to read (single-GPU
+ * engines; same bits as mode 0).  Mode 1 (a persistent kernel with a grid barrier per minibatch) lost
+ * to mode 0 at every batch size and was removed.                                                    */
 int f2v_set_epoch_mode(f2v_engine* e, int mode);
-/* Tuning knobs (integers; defaults are the measured optimum, profiles/r1_tune_v5.md):
+/* Tuning knobs (integers; defaults are the measured optimum, profiles/r1_tune_v5.md, r2_tune.md):
  *   "variant"   lane layout of the d=128 / d=64 kernels; -1 (default) = by launch size.  d=128:
  *               3 = 16 lanes per row, 2 rows in flight per group, 4 CTAs/SM at 64 registers;
  *               8 = the same at 5 CTAs/SM and 48 registers (launches with >= 48 K items);
  *               11 = 8 rows in flight at 128 registers (launches with < 12 K items); 0 = 4 rows in
- *               flight, 3 CTAs/SM.  d=64: 0 = 4 rows in flight, 1 = 2 rows in flight at 4 CTAs/SM,
- *               4 = at 5 CTAs/SM.
+ *               flight, 3 CTAs/SM; 21 / 22 = asynchronous shared-memory ring (cp.async stages, rows never
+ *               land in registers; neighbours and per-vertex negatives in one stream), 3 stages at
+ *               4 CTAs/SM / 4 stages at 3 CTAs/SM -- same bits, measured equal or slower (r2_tune.md).
+ *               d=64: 0 = 4 rows in flight, 1 = 2 rows in flight at 4 CTAs/SM, 4 = at 5 CTAs/SM, 21 / 22.
  *   "neg_smem"  0 disables the TMA staging of shared negatives (gathered from L2 instead)
  *   "par"       lane groups a minibatch should fill (adaptive chunk length, 0 = fixed chunk)
  *   "min_chunk" lower bound of the adaptive chunk length (0 = default: 16 for batches <= 8192, else 8)
  *   "pdl"       programmatic dependent launch of consecutive minibatches: 0 off, 1, 2 (default)
+ *   "auto_flow" epoch mode 0 switches to the dataflow epoch for batches up to this size (default 0 = never)
  *   "multicast" peer exchange through NVLink multicast stores: 1 (default) when supported, 0 never
+ *   "multicast_in_process"  1 = the engines of this process are each driven by their own host thread, so
+ *               they may set up the multicast exchange among themselves (f2v_train_gpus sets it)
  *   "sharded"   1 = row-sharded tables (set on every rank before f2v_comm_peer_export)
+ *   "peer_sig"  who publishes a minibatch's exchange step: 2 (default) = CTA 0 of the next launch after
+ *               its dependency wait; 1 = a 1-CTA kernel after the force kernel; 0 = the last CTA
  *   "trace"     1 = record per-minibatch times (f2v_trace_ms)
  *   "exchange_timeout_ms"  multi-GPU: how long a launch waits for a peer's exchange step before it
  *               gives up (default 30000; 0 = for ever); f2v_sync / f2v_get_embeddings then fail
- *   "order", "peer_sig", "peer_debug", "epoch_ctas"  development probes (tools/mgpu_probe.py)  */
+ *   "order", "peer_debug"  development probes (tools/mgpu_probe.py)                                  */
 int f2v_set_option(f2v_engine* e, const char* name, int64_t value);
 /* Kernel launches issued by this engine since creation (force + sampler kernels).     */
 uint64_t f2v_launch_count(const f2v_engine* e);
@@ -185,9 +195,12 @@ int f2v_comm_init(f2v_engine* e, const void* id128, int rank, int world);
  * Every rank maps the other ranks' tables (CUDA IPC between processes, direct peer access
  * between engines of one process); the kernel stores each finished row into its own replica
  * AND straight into every peer's replica over NVLink, so the transfer overlaps the compute row
- * by row; minibatches are separated by one system-scope flag per (rank, step) written by the
- * last CTA of a launch and polled at the start of the next launch -- no host round trip, no
- * collective call.  Rows of a minibatch are dealt to the ranks by a degree-balanced greedy
+ * by row.  Minibatches are separated by one system-scope step counter per rank: CTA 0 of launch
+ * b+1 publishes step b once launch b is complete (the launches stay chained by programmatic
+ * dependent launch), and a warp of launch b+1 waits for the peers' counters LAZILY -- only when
+ * the ids it is about to gather lie in a minibatch a peer has not published yet -- so the
+ * exchange latency hides behind the items that do not depend on the previous minibatch.  No host
+ * round trip, no collective call.  Rows of a minibatch are dealt to the ranks by a degree-balanced greedy
  * partition (no contiguity needed).  Results equal the single-GPU run bit for bit.
  *   1. every rank: f2v_comm_peer_export(e, blob)         blob: F2V_PEER_BLOB bytes
  *   2. the caller all-gathers the blobs in rank order (torch.distributed, MPI, a file ...)

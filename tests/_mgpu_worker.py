@@ -46,12 +46,14 @@ def main():
         # peer: NVLink multicast stores where the box supports them; peer_unicast: one store per peer
         # peer_fallback: rank 0 reports that the multicast object cannot be created -> all ranks go unicast
         # peer_sharded: row-sharded tables (each GPU stores 1/world of the rows, gathers cross NVLink)
-        for comm in ("peer", "peer_unicast", "peer_fallback", "peer_nopdl", "peer_sharded", "nccl"):
+        for comm in ("peer", "peer_multicast", "peer_unicast", "peer_fallback", "peer_nopdl", "peer_sharded", "nccl"):
             if comm == "peer_sharded" and world & (world - 1):
                 continue
             multi = F.Engine(rp, ci, dim, device=local)
             if comm == "peer_nopdl":
                 multi.set_option("pdl", 0)       # ordinary launches: every launch waits for the peers at kernel entry
+            if comm == "peer_multicast":
+                multi.set_option("multicast", 3)     # NVLink multicast stores also at N=2 (default there: one store per peer)
             if comm == "peer_unicast":
                 multi.set_option("multicast", 0)
             if comm == "peer_fallback":
@@ -67,7 +69,7 @@ def main():
                 dist.all_gather_object(blobs, multi.comm_peer_export())
                 multi.comm_peer_init(blobs, rank, world)
             a = run(multi)
-            if comm in ("peer", "peer_unicast"):
+            if comm in ("peer", "peer_multicast", "peer_unicast"):
                 # host-buffer epochs: every rank moves only its 1/world share of the table over PCIe
                 # (the rest travels over NVLink) and gets its share of the result back
                 per = -(-n // world)

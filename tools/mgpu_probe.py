@@ -18,9 +18,14 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     scale = int(os.environ.get("SCALE", "20"))
     model, dim, s = int(os.environ.get("MODEL", "6")), int(os.environ.get("DIM", "128")), 5
+    bs = int(os.environ.get("BS", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rp, ci = host.rmat_csr(scale, 16, 1)
+    if rank != 0:
+        dist.barrier()
+    rp, ci = host.rmat_csr_cached(scale, 16, 1)
+    if rank == 0:
+        dist.barrier()
     n = len(rp) - 1
     g = host.RandStream(1)
     X0 = g.init_embeddings(model, n, dim)
@@ -36,13 +41,14 @@ def main():
     batches = [int(x) for x in os.environ.get("BATCHES", "16384,65536").split(",")]
     chunks = [int(x) for x in os.environ.get("CHUNKS", "0").split(",")]
     for batch in batches:
-        neg = g.epoch_negatives(model, n, batch, s, 0).copy()
+        neg = g.epoch_negatives(model, n, batch, s, bs).copy()
         eng.set_negatives(neg)
         # variants with the flag barrier first: once it is off the ranks' step counters run free
         orders = [int(x) for x in os.environ.get("ORDERS", "0").split(",")]
-        variants = [(0, 1, o, 0, c) for c in chunks for o in orders]
+        sigs = [int(x) for x in os.environ.get("SIGS", "2").split(",")]
+        variants = [(0, sg, o, 0, c) for c in chunks for o in orders for sg in sigs]
         if batch == batches[-1] and os.environ.get("FREE", "1") == "1":
-            variants += [(2, 1, o, 0, chunks[-1]) for o in orders] + [(3, 1, 0, 0, chunks[-1])]
+            variants += [(1, 2, orders[0], 0, chunks[-1]), (2, 2, orders[0], 0, chunks[-1]), (3, 2, orders[0], 0, chunks[-1])]
         for dbg, sig, persist, mode, chunk in variants:
             eng.set_option("peer_debug", dbg)
             eng.set_option("peer_sig", sig)
@@ -53,7 +59,7 @@ def main():
                 eng.set_negative_offset(0)
                 dist.barrier()
                 torch.cuda.synchronize()
-                eng.run_epoch(model, batch, s, 0, 0.02, chunk)
+                eng.run_epoch(model, batch, s, bs, 0.02, chunk)
                 ms.append(eng.last_epoch_ms())
                 if dbg & 2:
                     dist.barrier()
@@ -62,18 +68,21 @@ def main():
                 eng.set_negative_offset(0)
                 dist.barrier()
                 torch.cuda.synchronize()
-                eng.run_epoch(model, batch, s, 0, 0.02, chunk)
+                eng.run_epoch(model, batch, s, bs, 0.02, chunk)
                 tr = eng.trace_ms()
                 eng.set_option("trace", 0)
                 allt = [None] * world
                 dist.all_gather_object(allt, [round(float(x) * 1e3, 1) for x in tr])
                 if rank == 0:
                     for r_, t_ in enumerate(allt):
-                        print(json.dumps({"trace_us_rank": r_, "dbg": dbg, "order": persist, "us": t_}), flush=True)
+                        nb_ = len(t_)
+                        q_ = [round(sum(t_[k * nb_ // 4:(k + 1) * nb_ // 4]) / 1e3, 3) for k in range(4)]
+                        print(json.dumps({"trace_rank": r_, "dbg": dbg, "order": persist, "chunk": chunk, "quartile_ms": q_,
+                                          "first8_us": t_[:8], "last4_us": t_[-4:]}), flush=True)
             t = torch.tensor([min(ms[2:])], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "mode": mode, "chunk": chunk, "order": persist,
+                print(json.dumps({"world": world, "B": batch, "peer_debug": dbg, "peer_sig": sig, "mode": mode, "chunk": chunk, "order": persist,
                                   "ms": float(t.item()), "rank0_ms": [round(x, 3) for x in ms]}), flush=True)
     dist.barrier()
     eng.close()
