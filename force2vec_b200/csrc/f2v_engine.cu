@@ -1000,11 +1000,15 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     if (e->world > 1 && !e->peer_mode && batch % e->world)
         return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
     CU(cudaSetDevice(e->device));
-    // default hub chunk: 128 edges; 64 on a multi-GPU engine whose share of a minibatch is small enough
-    // (< 16 K rows per rank) for the longest item to be the critical path (measured at N=4 on R-MAT 20;
-    // with large shares shorter chunks only add partial-sum traffic: R-MAT 24, N=2, 256 K rows per
-    // minibatch: 24.6 ms per epoch at 128, 26.9 at 64, 29.1 at 32 -- profiles/r2_mgpu_cfg4.md)
-    if (chunk == 0) chunk = (e->world > 1 && batch / (uint32_t)e->world < 16384u) ? 64 : 128;
+    // default hub chunk (upper bound of the adaptive chunk length): 256 edges for rows of >= 512 bytes, 128 for
+    // shorter rows; 64 on a multi-GPU engine whose share of a minibatch is small enough (< 16 K rows per rank)
+    // for the longest item to be the critical path.  Measured (profiles/r2_tune.md section 8): R-MAT 20 d=128
+    // B=65536: 1.76 / 1.65 / 1.74 / 1.80 ms at 128 / 256 / 512 / 1024; R-MAT 24 d=128: 40.8 / 39.2 / 38.9 / 37.9;
+    // R-MAT 22 d=64: 4.73 ms at 128, 6.52 at 1024; R-MAT 24, N=2: 24.6 at 128, 26.9 at 64, 29.1 at 32.
+    if (chunk == 0) {
+        chunk = e->dim >= 128 ? 256 : 128;
+        if (e->world > 1 && batch / (uint32_t)e->world < 16384u) chunk = 64;
+    }
     const uint64_t nb = (e->n + batch - 1) / batch;
     const uint64_t W = neg_stride(model, batch, s, bs_mode);
     if (e->neg_count < e->neg_off + nb * W)

@@ -103,8 +103,8 @@ typedef struct f2v_train_args {
 int f2v_train(const f2v_train_args* a, float* X_out, double* seconds);
 /* The same run on devices a->device .. a->device+gpus-1 of this node, driven from this process
  * (one host thread per GPU; replicated tables, the exchange fused into the force kernel).  The
- * result equals f2v_train's bit for bit for equal `chunk` (0 = default differs: 128 on one GPU,
- * 64 on several).  gpus <= 1 is f2v_train.                                                 */
+ * result equals f2v_train's bit for bit for equal `chunk` (0 = the default, which differs when a
+ * rank's share of a minibatch is below 16 K rows: 64 instead of 256 / 128).  gpus <= 1 is f2v_train.                                                 */
 int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, double* seconds);
 
 #ifdef __cplusplus
