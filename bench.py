@@ -595,6 +595,13 @@ def extra_lines(torch, F, host, a, peak):
                 key = name if bsz == WORKLOADS[name]["batch"] else "%s_B%d" % (name, bsz)
                 out[key] = {"workload": workload_name(b), "epoch_ms": ms, "pairs_per_s": pairs_per_epoch(b, n, nnz) / ms * 1e3,
                             "frac_algorithmic": bytes_per_epoch(b, n, nnz) / ms / 1e6 / peak}
+                if b.model == 7:
+                    # the epoch above uses the device walk sampler (`-walk 1`); the product default `-walk 0` draws the
+                    # walks off the libc-compatible stream on the host, serially by construction (algorithms.cpp:1097-1118:
+                    # the draws a walk consumes depend on its path) -- that, not the GPU, bounds an epoch of `-walk 0`
+                    t0 = time.time()
+                    g.walks(rp, ci)
+                    out[key]["host_walks_ms_walk0"] = (time.time() - t0) * 1e3
     # cfg1: the reference's README command (cora, option 5, d=128, batch 256, 1200 iterations) through the
     # whole-run driver f2v_train (init + epochs + download, the span the reference itself times)
     mtx = os.path.join(ROOT, "tests", "golden", "cora.mtx")

@@ -405,15 +405,14 @@ static int build_plan(f2v_engine* e, Plan& pl, uint64_t first_row, uint64_t nrow
 }
 
 // ------------------------------------------------------------------ dispatch -----------
-template <class L, int MODEL, bool PERSIST>
-static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_count) {
+template <class L, int MODEL>
+static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st, int sm_count) {
+    (void)sm_count;
     if (p.n_items == 0) return cudaSuccess;
-    auto kern = force_batch_kernel<L, MODEL, PERSIST>;
+    auto kern = force_batch_kernel<L, MODEL>;
     const bool negs = L::kBulk && p.neg_in_smem;
-    const bool lut_s = PERSIST && MODEL != kTDist && L::kBulk;
     size_t smem = 0;
-    if (negs || lut_s || L::kStages > 0)
-        smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0) + (lut_s ? kLutAlloc * sizeof(float) : 0);
+    if (negs || L::kStages > 0) smem = 128 + (negs ? (size_t)p.s * p.dim * sizeof(float) : 0);
     if constexpr (L::kStages > 0) {
         smem += L::kCtaBytes;                        // the lane groups' asynchronous-copy rings
         static bool carve = false;                   // (per instantiation) all of the SM's L1/shared array as shared
@@ -428,13 +427,7 @@ static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_
         if (e != cudaSuccess) return e;
     }
     const unsigned per_cta = kWarpsPerCta * L::G;
-    unsigned grid = (p.n_items + per_cta - 1) / per_cta;
-    if (PERSIST) {
-        int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
-        if (e != cudaSuccess) return e;
-        grid = std::min<unsigned>(grid, (unsigned)(sm_count * std::max(per_sm, 1)));
-    }
+    const unsigned grid = (p.n_items + per_cta - 1) / per_cta;
     if (p.pdl) {
         // programmatic dependent launch: may be scheduled while the previous minibatch drains
         cudaLaunchConfig_t cfg = {};
@@ -447,11 +440,6 @@ static cudaError_t launch_batch_k(const BatchParams& p, cudaStream_t st, int sm_
     }
     kern<<<grid, kWarpsPerCta * 32, smem, st>>>(p);
     return cudaGetLastError();
-}
-
-template <class L, int MODEL>
-static cudaError_t launch_batch_t(const BatchParams& p, cudaStream_t st, int sm_count) {
-    return launch_batch_k<L, MODEL, false>(p, st, sm_count);
 }
 
 template <class L>

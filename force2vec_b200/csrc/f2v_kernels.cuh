@@ -461,17 +461,11 @@ __device__ __forceinline__ float clamp5(float v) { return fminf(fmaxf(v, -5.0f),
 // fast_SM(), algorithms.cpp:766-770; sum and product in double, truncation, no interpolation.
 // Branch-free: the index is taken from v clamped to [-6, 6] (entry 2048 exists and is 1.0f),
 // then the reference's two range tests select 1 / 0.
-template <bool LS>
 __device__ __forceinline__ float fast_sm(const float* __restrict__ lut, float v) {
     const double res = (double)(float)(kLutSize / 12.0);   // SM_RESOLUTION, algorithms.h:49
     const float vc = fminf(fmaxf(v, -6.0f), 6.0f);
     const int i = (int)(((double)vc + 6.0) * res);
-    float sg;
-    if (LS) {   // table staged in shared memory (persistent CTAs)
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sg) : "r"(smem_u32(lut) + 4u * (uint32_t)i));
-    } else {
-        sg = __ldg(lut + i);
-    }
+    float sg = __ldg(lut + i);
     sg = v > 6.0f ? 1.0f : sg;
     sg = v < -6.0f ? 0.0f : sg;
     return sg;
@@ -488,11 +482,11 @@ __device__ __forceinline__ float group_sum(float x) {
 //   option 5: the factor d1 (algorithms.cpp:608 d1 = -2.0/(1.0+attrc); :622 d1 = 2.0/(repuls*(1.0+repuls)))
 //   option 6/7: the coefficient of x_p: attractive STEP*degi*(1.0-sigma) formed in double and
 //   rounded once (:866) == fma(-sd, sg, sd); repulsive STEP*sigma in float (:908)
-template <int MODEL, bool ATTR, bool LS>
+template <int MODEL, bool ATTR>
 __device__ __forceinline__ float pair_scalar(float r, float lr, float sd, const float* __restrict__ lut) {
     if (MODEL == kTDist)
         return ATTR ? __fdiv_rn(-2.0f, __fadd_rn(1.0f, r)) : __fdiv_rn(2.0f, __fmul_rn(r, __fadd_rn(1.0f, r)));
-    const float sg = fast_sm<LS>(lut, r);
+    const float sg = fast_sm(lut, r);
     return ATTR ? fmaf(-sd, sg, sd) : __fmul_rn(lr, sg);
 }
 
@@ -520,14 +514,14 @@ __device__ __forceinline__ void pair_apply(float (&acc)[L::NE], const float (&xp
 // One (i, p) pair per group.  ATTR: attractive (neighbour / walk sample) or repulsive (negative).
 // Executed by the whole warp (the reduction shuffles are warp-wide); groups with nothing to do
 // pass valid = false and contribute exactly zero.
-template <class L, int MODEL, bool ATTR, bool LS>
+template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&xi)[L::NE],
                                             const float (&xp)[L::NE], bool valid, float lr, float sd,
                                             const float* __restrict__ lut) {
     float d[L::NE];
     float r = MODEL == kTDist ? L::diff_ss(d, xi, xp) : L::dot(xi, xp);
     r = group_sum<L::LPR>(r);
-    const float sc = pair_scalar<MODEL, ATTR, LS>(r, lr, sd, lut);
+    const float sc = pair_scalar<MODEL, ATTR>(r, lr, sd, lut);
     const bool clampless = MODEL == kTDist && !__any_sync(kFull, may_clamp(r, ATTR, valid));
     pair_apply<L, MODEL, ATTR>(acc, xp, d, sc, valid, lr, clampless);
 }
@@ -536,7 +530,7 @@ __device__ __forceinline__ void pair_update(float (&acc)[L::NE], const float (&x
 // (lower half of the group ends up with pair 0's total, upper half with pair 1's: log2(LPR)
 // shuffles for both instead of 2*log2(LPR)), each half evaluates the scalar of ITS pair once,
 // and one more shuffle swaps the results.  Updates are applied in pair order (0 then 1).
-template <class L, int MODEL, bool ATTR, bool LS>
+template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const float (&x0)[L::NE], const float (&x1)[L::NE],
                                              bool v0, bool v1, float lr, float sd,
@@ -550,7 +544,7 @@ __device__ __forceinline__ void pair2_update(float (&acc)[L::NE], const float (&
     keep += __shfl_xor_sync(kFull, hi ? p0 : p1, H);
 #pragma unroll
     for (int off = H / 2; off >= 1; off >>= 1) keep += __shfl_xor_sync(kFull, keep, off);
-    const float mine = pair_scalar<MODEL, ATTR, LS>(keep, lr, sd, lut);
+    const float mine = pair_scalar<MODEL, ATTR>(keep, lr, sd, lut);
     const float other = __shfl_xor_sync(kFull, mine, H);
     const float s0 = hi ? other : mine, s1 = hi ? mine : other;
     // (each half of the group holds the reduced r of ITS pair: one vote covers both pairs of every group)
@@ -643,7 +637,7 @@ __device__ __forceinline__ void lazy_peer_wait(const BatchParams& p, uint32_t ne
 // Every group gathers its own `cnt` rows named by idx[0..cnt) (in order) and folds them into
 // its acc.  Indices are fetched LPR at a time per group (coalesced) and broadcast inside the
 // group by shuffle; U row loads per group (G*U per warp) are in flight.
-template <class L, int MODEL, bool ATTR, bool LS>
+template <class L, int MODEL, bool ATTR>
 __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&xi)[L::NE],
                                              const uint32_t* __restrict__ idx, uint32_t cnt,
                                              uint32_t self, const BatchParams& p, uint32_t split, float sd, int l,
@@ -679,12 +673,12 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
             if (U % 2 == 0) {
 #pragma unroll
                 for (int u = 0; u < U; u += 2)
-                    pair2_update<L, MODEL, ATTR, LS>(acc, xi, rows[u], rows[u + 1 < U ? u + 1 : u], valid[u],
+                    pair2_update<L, MODEL, ATTR>(acc, xi, rows[u], rows[u + 1 < U ? u + 1 : u], valid[u],
                                                      valid[u + 1 < U ? u + 1 : u], p.lr, sd, lut, l);
             } else {
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    pair_update<L, MODEL, ATTR, LS>(acc, xi, rows[u], valid[u], p.lr, sd, lut);
+                    pair_update<L, MODEL, ATTR>(acc, xi, rows[u], valid[u], p.lr, sd, lut);
             }
         }
     }
@@ -695,13 +689,13 @@ __device__ __forceinline__ void gather_pairs(float (&acc)[L::NE], const float (&
 // the unified row stream of gather_stream() mixes an item's neighbours and its per-vertex negatives,
 // and the lane groups of a warp sit at different positions of their streams.  Arithmetic identical
 // to the templated versions above, operation for operation.
-template <int MODEL, bool LS>
+template <int MODEL>
 __device__ __forceinline__ float pair_scalar_rt(float r, bool attr, float lr, float sd, const float* __restrict__ lut) {
     if (MODEL == kTDist) {
         const float one_r = __fadd_rn(1.0f, r);
         return __fdiv_rn(attr ? -2.0f : 2.0f, attr ? one_r : __fmul_rn(r, one_r));
     }
-    const float sg = fast_sm<LS>(lut, r);
+    const float sg = fast_sm(lut, r);
     return attr ? fmaf(-sd, sg, sd) : __fmul_rn(lr, sg);
 }
 template <class L, int MODEL>
@@ -714,7 +708,7 @@ __device__ __forceinline__ void pair_apply_rt(float (&acc)[L::NE], const float (
     else if (attr) L::axpy(acc, valid ? sc : 0.f, xp);
     else L::sub_mul(acc, valid ? sc : 0.f, xp);
 }
-template <class L, int MODEL, bool LS>
+template <class L, int MODEL>
 __device__ __forceinline__ void pair2_update_rt(float (&acc)[L::NE], const float (&xi)[L::NE],
                                                 const float (&x0)[L::NE], const float (&x1)[L::NE],
                                                 bool v0, bool v1, bool a0, bool a1, float lr, float sd,
@@ -728,7 +722,7 @@ __device__ __forceinline__ void pair2_update_rt(float (&acc)[L::NE], const float
     keep += __shfl_xor_sync(kFull, hi ? p0 : p1, H);
 #pragma unroll
     for (int off = H / 2; off >= 1; off >>= 1) keep += __shfl_xor_sync(kFull, keep, off);
-    const float mine = pair_scalar_rt<MODEL, LS>(keep, hi ? a1 : a0, lr, sd, lut);
+    const float mine = pair_scalar_rt<MODEL>(keep, hi ? a1 : a0, lr, sd, lut);
     const float other = __shfl_xor_sync(kFull, mine, H);
     const float s0 = hi ? other : mine, s1 = hi ? mine : other;
     const bool clampless = MODEL == kTDist && !__any_sync(kFull, may_clamp(keep, hi ? a1 : a0, hi ? v1 : v0));
@@ -745,7 +739,7 @@ __device__ __forceinline__ void pair2_update_rt(float (&acc)[L::NE], const float
 // Ids are fetched LPR at a time (one coalesced load per group), one block ahead of the copy pointer.
 // All groups of the warp run the same number of stages (the reductions are warp-wide); slots past a
 // group's own stream are zero-filled without touching memory and contribute exactly zero.
-template <class L, int MODEL, bool LS>
+template <class L, int MODEL>
 __device__ __forceinline__ void gather_stream(float (&acc)[L::NE], const float (&xi)[L::NE],
                                               const uint32_t* __restrict__ idxA, uint32_t cntA,
                                               const uint32_t* __restrict__ idxB, uint32_t cntB,
@@ -818,7 +812,7 @@ __device__ __forceinline__ void gather_stream(float (&acc)[L::NE], const float (
             x1[4 * c + 0] = b.x; x1[4 * c + 1] = b.y; x1[4 * c + 2] = b.z; x1[4 * c + 3] = b.w;
         }
         const uint32_t q0 = 2u * k;
-        pair2_update_rt<L, MODEL, LS>(acc, xi, x0, x1, q0 < cnt, q0 + 1 < cnt, q0 < cntA, q0 + 1 < cntA, p.lr, sd, lut, l);
+        pair2_update_rt<L, MODEL>(acc, xi, x0, x1, q0 < cnt, q0 + 1 < cnt, q0 < cntA, q0 + 1 < cntA, p.lr, sd, lut, l);
     }
     cp_async_wait<0>();
 }
@@ -870,9 +864,9 @@ __device__ __forceinline__ void publish_predecessor(const BatchParams& p) {
 
 // G work items, one per group: items t_base .. t_base+G-1 (groups past n_items idle).
 // s_neg: the staged negative rows (bs=0) or nullptr; neg_bar: their mbarrier.
-template <class L, int MODEL, bool LS>
+template <class L, int MODEL>
 __device__ __forceinline__ void process_items(const BatchParams& p, const BatchVar& bv, uint32_t t_base,
-                                              const float* s_neg, uint64_t* neg_bar, uint32_t neg_parity, int lane,
+                                              const float* s_neg, uint64_t* neg_bar, int lane,
                                               const float* __restrict__ lut, uint32_t ring_base, uint32_t& rows_ok) {
     constexpr int NE = L::NE, LPR = L::LPR;
     constexpr bool kRing = L::kStages > 0;
@@ -931,9 +925,9 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
     uint32_t ring = 0;
     if constexpr (kRing) {
         ring = ring_base + (uint32_t)(((threadIdx.x >> 5) * L::G + g) * L::kGroupBytes);
-        gather_stream<L, MODEL, LS>(acc, xi, nbr, nbr_cnt, nidx, negB, v, p, bv.split, sd, l, lut, ring, rows_ok, early_idx, first);
+        gather_stream<L, MODEL>(acc, xi, nbr, nbr_cnt, nidx, negB, v, p, bv.split, sd, l, lut, ring, rows_ok, early_idx, first);
     } else {
-        gather_pairs<L, MODEL, true, LS>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, rows_ok, early_idx, first);
+        gather_pairs<L, MODEL, true>(acc, xi, nbr, nbr_cnt, v, p, bv.split, sd, l, lut, rows_ok, early_idx, first);
     }
 
     // split rows: publish this chunk's partial sum; the last chunk of a fold block (kFoldBlock
@@ -981,27 +975,27 @@ __device__ __forceinline__ void process_items(const BatchParams& p, const BatchV
 
     // repulsive part: s negatives (algorithms.cpp:614-627, 898-911, 1172-1183)
     if (s_neg != nullptr) {
-        mbar_wait(neg_bar, neg_parity);
+        mbar_wait(neg_bar, 0);
         uint32_t q = 0;
         for (; q + 2 <= p.s; q += 2) {
             float r0[NE], r1[NE];
             L::load_s(r0, s_neg + (size_t)q * rs, l, p.dim);
             L::load_s(r1, s_neg + (size_t)(q + 1) * rs, l, p.dim);
-            pair2_update<L, MODEL, false, LS>(acc, xi, r0, r1, finish, finish, p.lr, sd, lut, l);
+            pair2_update<L, MODEL, false>(acc, xi, r0, r1, finish, finish, p.lr, sd, lut, l);
         }
         if (q < p.s) {
             float row[NE];
             L::load_s(row, s_neg + (size_t)q * rs, l, p.dim);
-            pair_update<L, MODEL, false, LS>(acc, xi, row, finish, p.lr, sd, lut);
+            pair_update<L, MODEL, false>(acc, xi, row, finish, p.lr, sd, lut);
         }
     } else if constexpr (kRing) {
         // rows that were not split took their negatives in the stream above; a split row's negatives
         // follow the fold (the chunk that finished the row)
         if (any_chunk)
-            gather_stream<L, MODEL, LS>(acc, xi, nbr, 0u, nidx, (is_chunk && finish) ? p.s : 0u, v, p, bv.split, sd, l, lut,
+            gather_stream<L, MODEL>(acc, xi, nbr, 0u, nidx, (is_chunk && finish) ? p.s : 0u, v, p, bv.split, sd, l, lut,
                                         ring, rows_ok, false, 0u);
     } else {
-        gather_pairs<L, MODEL, false, LS>(acc, xi, nidx, finish ? p.s : 0u, v, p, bv.split, sd, l, lut, rows_ok);
+        gather_pairs<L, MODEL, false>(acc, xi, nidx, finish ? p.s : 0u, v, p, bv.split, sd, l, lut, rows_ok);
     }
     if (finish) {
         if (MODEL == kTDist || is_chunk) {
@@ -1075,35 +1069,29 @@ __device__ __forceinline__ void stage_negatives(const BatchParams& p, const Batc
 }
 
 // ------------------------------------------------------------------ kernels ------------
-// One launch per minibatch.  PERSIST = false: one group of lanes per item and one pass per CTA,
-// the hardware CTA scheduler balances the load.  PERSIST = true: the grid is sized to the
-// machine (SMs x resident CTAs), every warp strides over the item list (items are ordered hub
-// chunks first, then rows by descending degree class, so round-robin is longest-first), and
-// the per-CTA staging -- the minibatch's negative rows and, for the sigmoid models, the LUT,
-// all by TMA bulk copies on one mbarrier -- is paid once per CTA instead of once per 16 items.
-template <class L, int MODEL, bool PERSIST>
+// One launch per minibatch: one group of lanes per item and one pass per CTA; the hardware CTA scheduler
+// balances the load (items are ordered hub chunks first, then rows by descending degree class, so it is
+// longest-first).  The minibatch's shared negative rows (bs=0) are staged once per CTA by TMA bulk copies.
+template <class L, int MODEL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, L::MINB)
 force_batch_kernel(const BatchParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr bool LS = PERSIST && MODEL != kTDist && L::kBulk;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const bool negs = L::kBulk && p.neg_in_smem;
     float* s_neg = negs ? reinterpret_cast<float*>(smem_raw + 128) : nullptr;
     const uint32_t neg_bytes = negs ? (uint32_t)(p.s * L::stride(p.dim) * sizeof(float)) : 0u;
-    const float* lut = p.lut;
     const BatchVar bv = batch_var(p);
     if (!p.late_wait) { publish_predecessor(p); peer_wait(p); }
-    if (negs || LS) {
+    if (negs) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
         if (threadIdx.x < 32) {
-            const uint32_t lut_bytes = LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u;
-            if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes + lut_bytes);
+            if (threadIdx.x == 0) mbar_expect_tx(bar, neg_bytes);
             if (p.pdl) pdl_wait();                  // negative rows may have been written by the previous minibatch
             if (p.late_wait) {
                 publish_predecessor(p);
                 uint32_t need = 0, ro = 0;                 // the staged negative rows that lie below the split
-                for (uint32_t q = threadIdx.x; negs && q < p.s; q += 32) {
+                for (uint32_t q = threadIdx.x; q < p.s; q += 32) {
                     const uint32_t jn = __ldcg(bv.neg + q);
                     if (jn < bv.split) need = max(need, jn + 1u);
                 }
@@ -1111,34 +1099,23 @@ force_batch_kernel(const BatchParams p) {
             }
             if (p.wait_step || p.pdl) fence_proxy_async();   // rows written with generic stores (here or by peers) are read by TMA next
             __syncwarp();
-            if (negs) stage_negatives<L>(p, bv, s_neg, bar);
-            if (LS && threadIdx.x == 31) bulk_g2s(smem_raw + 128 + neg_bytes, p.lut, lut_bytes, bar);
-        }
-        if (LS) {
-            lut = reinterpret_cast<const float*>(smem_raw + 128 + neg_bytes);
-            mbar_wait(bar, 0);      // the table is needed by the first attractive pair
+            stage_negatives<L>(p, bv, s_neg, bar);
         }
     }
     const int lane = threadIdx.x & 31;
     const uint32_t gw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    // asynchronous-ring layouts: the lane groups' rings follow the staged negatives / table
-    const uint32_t ring_base = smem_u32(smem_raw) + 128u + neg_bytes + (LS ? (uint32_t)(kLutAlloc * sizeof(float)) : 0u);
+    // asynchronous-ring layouts: the lane groups' rings follow the staged negatives
+    const uint32_t ring_base = smem_u32(smem_raw) + 128u + neg_bytes;
     uint32_t rows_ok = 0;
-    if (p.late_wait && !(negs || LS) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (p.late_wait && !negs && blockIdx.x == 0 && threadIdx.x == 0) {
         // no staging warp in this launch: thread 0 of CTA 0 publishes the predecessor's step itself
         if (p.pdl) pdl_wait();
         publish_predecessor(p);
     }
-    if (PERSIST) {
-        const uint32_t stride = gridDim.x * kWarpsPerCta * L::G;
-        for (uint32_t t_base = gw * L::G; t_base < bv.n_items; t_base += stride)
-            process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base, rows_ok);
-    } else {
-        const uint32_t t_base = gw * L::G;
-        if (t_base < bv.n_items) process_items<L, MODEL, LS>(p, bv, t_base, s_neg, bar, 0, lane, lut, ring_base, rows_ok);
-    }
+    const uint32_t t_base = gw * L::G;
+    if (t_base < bv.n_items) process_items<L, MODEL>(p, bv, t_base, s_neg, bar, lane, p.lut, ring_base, rows_ok);
     // the CTA's shared memory must stay allocated until the bulk copies have landed
-    if (negs || LS) mbar_wait(bar, 0);
+    if (negs) mbar_wait(bar, 0);
     peer_signal(p);
 }
 
@@ -1187,7 +1164,7 @@ force_flow_kernel(const FlowParams fp) {
             bv.split = b * p.flow_batch;
             bv.lo = bv.split;
             bv.neg = p.neg + (size_t)b * fp.neg_stride;
-            process_items<L, MODEL, false>(p, bv, t_base, nullptr, nullptr, 0, lane, p.lut, 0u, rows_ok);
+            process_items<L, MODEL>(p, bv, t_base, nullptr, nullptr, lane, p.lut, 0u, rows_ok);
         }
     }
 }

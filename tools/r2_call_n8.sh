@@ -1,0 +1,17 @@
+set -x
+O=gpurun_out/r2n8
+mkdir -p $O
+nvidia-smi --query-gpu=index,name,memory.total --format=csv > $O/gpus.txt; free -g >> $O/gpus.txt; df -h /dev/shm >> $O/gpus.txt
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+# cfg4 at N=8 (the headline workload of the scaling run)
+timeout 600 $TR --master-port 29711 bench.py --gpus 8 --no-extra > $O/bench_cfg4_n8.json 2> $O/bench_cfg4_n8.err; tail -2 $O/bench_cfg4_n8.err; python -c "
+import json;d=json.load(open('$O/bench_cfg4_n8.json'));print('cfg4 N8 ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],'parity',d['parity']['bit_exact'])"
+# cfg5: R-MAT-26, replicated tables (fits: 2 x 32 GiB + 9 GiB CSR per GPU), with the 1-GPU-vs-8-GPU check
+timeout 1500 $TR --master-port 29712 bench.py --gpus 8 --workload cfg5 --steps 3 --warmup 2 --no-extra > $O/bench_cfg5_n8_replicated.json 2> $O/bench_cfg5_n8_replicated.err
+rc=$?; tail -3 $O/bench_cfg5_n8_replicated.err; cut -c1-1500 $O/bench_cfg5_n8_replicated.json
+if [ $rc -ne 0 ]; then
+  timeout 1500 $TR --master-port 29714 bench.py --gpus 8 --workload cfg5 --steps 3 --warmup 2 --no-extra --multicast 0 > $O/bench_cfg5_n8_replicated_unicast.json 2> $O/bench_cfg5_n8_replicated_unicast.err; tail -3 $O/bench_cfg5_n8_replicated_unicast.err; cut -c1-1500 $O/bench_cfg5_n8_replicated_unicast.json
+fi
+# cfg5 row-sharded (what BASELINE names): each GPU stores 1/8 of both tables
+timeout 1500 $TR --master-port 29713 bench.py --gpus 8 --workload cfg5 --sharded 1 --steps 2 --warmup 1 --no-extra > $O/bench_cfg5_n8_sharded.json 2> $O/bench_cfg5_n8_sharded.err; tail -3 $O/bench_cfg5_n8_sharded.err; cut -c1-1500 $O/bench_cfg5_n8_sharded.json
+ls -la /dev/shm | head; du -sh $O
