@@ -988,13 +988,13 @@ static int run_epoch_impl(f2v_engine* e, int model, uint32_t batch, uint32_t s, 
     if (e->world > 1 && !e->peer_mode && batch % e->world)
         return fail(F2V_ERR_ARG, "batch (%u) must be a multiple of the world size (%d)", batch, e->world);
     CU(cudaSetDevice(e->device));
-    // default hub chunk (upper bound of the adaptive chunk length): 256 edges for rows of >= 512 bytes, 128 for
-    // shorter rows; 64 on a multi-GPU engine whose share of a minibatch is small enough (< 16 K rows per rank)
+    // default hub chunk (upper bound of the adaptive chunk length): 256 edges for rows of >= 512 bytes in batches
+    // of >= 16 K rows, else 128; 64 on a multi-GPU engine whose share of a minibatch is small enough (< 16 K rows per rank)
     // for the longest item to be the critical path.  Measured (profiles/r2_tune.md section 8): R-MAT 20 d=128
     // B=65536: 1.76 / 1.65 / 1.74 / 1.80 ms at 128 / 256 / 512 / 1024; R-MAT 24 d=128: 40.8 / 39.2 / 38.9 / 37.9;
     // R-MAT 22 d=64: 4.73 ms at 128, 6.52 at 1024; R-MAT 24, N=2: 24.6 at 128, 26.9 at 64, 29.1 at 32.
     if (chunk == 0) {
-        chunk = e->dim >= 128 ? 256 : 128;
+        chunk = (e->dim >= 128 && batch >= 16384u) ? 256 : 128;     // (small batches: R-MAT 20, B=256: 33 ms at 128, 36 at 256)
         if (e->world > 1 && batch / (uint32_t)e->world < 16384u) chunk = 64;
     }
     const uint64_t nb = (e->n + batch - 1) / batch;

@@ -775,10 +775,11 @@ extern "C" int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, d
     const int model = a->option;
     const int bs = model == F2V_WALK ? 0 : (a->bs ? 1 : 0);
     const int G = gpus;
-    auto t0 = std::chrono::steady_clock::now();
+    // the timed span is f2v_train's (and the reference's, algorithms.cpp:557-647): it starts after the engines
+    // exist -- the reference's constructor has copied the graph before its timer starts -- and before the init draws
+    std::chrono::steady_clock::time_point t0;
     f2v_rng* g = f2v_rng_create(a->seed);
     if (!g) return f2v::host_fail(F2V_ERR_NOMEM, "f2v_train_gpus: out of host memory");
-    f2v_init_embeddings(g, model, a->n, a->dim, X_out);
     float lut[F2V_LUT_SIZE];
     f2v_build_lut(lut);
     const uint64_t slen = f2v_neg_stream_len(model, a->n, a->batch, a->nsamples, bs);
@@ -803,6 +804,11 @@ extern "C" int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, d
         if (!rc) step(f2v_comm_peer_export(e, blobs.data() + (size_t)r * F2V_PEER_BLOB));
         bool stop = bar.wait();
         if (!stop) step(f2v_comm_peer_init(e, blobs.data(), r, G));
+        stop = bar.wait();
+        if (r == 0) {                        // engines and exchange are up: the timed span starts with the init draws
+            t0 = std::chrono::steady_clock::now();
+            if (!stop) step(f2v_init_embeddings(g, model, a->n, a->dim, X_out));
+        }
         stop = bar.wait();
         if (!stop) {
             if (model != F2V_TDIST) step(f2v_set_lut(e, lut, F2V_LUT_SIZE));
@@ -883,6 +889,7 @@ std::vector<float> algorithms::run(int option, int bs, uint32_t iters, uint32_t 
     a.n = graph.rows; a.nnz = graph.nnz; a.rowptr = graph.rowptr.data(); a.colids = graph.colids.data();
     a.dim = DIM; a.option = option; a.bs = bs; a.iterations = iters; a.batch = batch; a.nsamples = ns;
     a.lr = lr; a.seed = seed; a.device = device; a.walk_sampler = walk_sampler; a.epoch_mode = epoch_mode;
+    a.chunk = chunk;
     double sec = 0;
     int rc = gpus > 1 ? f2v_train_gpus(&a, gpus, nCoordinates.data(), &sec) : f2v_train(&a, nCoordinates.data(), &sec);
     if (rc != F2V_OK) {

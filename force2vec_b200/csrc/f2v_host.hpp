@@ -36,6 +36,7 @@ public:
     int gpus = 1;                      // > 1: devices device..device+gpus-1, minibatches split across them
     int epoch_mode = 0;                // engine execution mode (include/f2v.h f2v_set_epoch_mode)
     int walk_sampler = 0;              // 0 = libc-stream host walks, 1 = device sampler
+    uint32_t chunk = 0;                // hub-row chunk length (0 = default; equal values give equal bits on any GPU count)
     uint32_t seed = 1;                 // Test/Force2Vec.cpp:126 srand(1)
 
     algorithms(const Csr& A_csr, std::string input, std::string outputd, uint32_t dim, float gm, uint32_t bsize);

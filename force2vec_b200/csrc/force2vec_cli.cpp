@@ -2,7 +2,7 @@
 // Same flags, defaults, stdout lines, output-file naming and Results.txt row as the
 // reference driver (/root/reference/Test/Force2Vec.cpp:22-47 help, :54-116 argv loop,
 // :121-150 dispatch, :191-198 Results.txt), for options 5, 6 and 7; the force step runs
-// on the GPU.  Extra flags (ignored by the reference): -device <int>, -gpus <int>, -mode <0|1>
+// on the GPU.  Extra flags (ignored by the reference): -device <int>, -gpus <int>, -mode <0|2>, -chunk <int>
 // (engine epoch mode), -walk <0|1> (0 = libc-stream host walks, 1 = device sampler).
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +36,7 @@ static void helpmessage() {
     printf("-device <int>, (first) CUDA device. (default:0)\n");
     printf("-gpus <int>, number of GPUs; minibatches are split across them. (default:1)\n");
     printf("-mode <int>, 0 = one launch per minibatch, 2 = one dataflow launch per epoch. (default:0)\n");
+    printf("-chunk <int>, hub rows longer than this are split across warps; equal values give equal bits on any GPU count. (default:0 = auto)\n");
     printf("-walk <int>, option 7 walks: 0 = host (reference stream), 1 = device sampler. (default:0)\n");
     printf("-h, show help message.\n");
 }
@@ -44,7 +45,7 @@ int main(int argc, char* argv[]) {
     float gamma = 1.0f, lr = 0.02f;
     uint32_t batchsize = 384, iterations = 1200, numberOfThreads = (uint32_t)omp_get_max_threads(), dim = 128,
              option = 5, nsamples = 5, bs = 0;
-    int device = 0, mode = 0, walk = 0, gpus = 1;
+    int device = 0, mode = 0, walk = 0, gpus = 1, chunk = 0;
     string inputfile = "", outputfile = "", algoname = "Force2Vec:t-distribution with negative sampling",
            initname = "RAND";
     for (int p = 0; p < argc; p++) {
@@ -65,6 +66,7 @@ int main(int argc, char* argv[]) {
         else if (strcmp(argv[p], "-gpus") == 0) gpus = atoi(argv[p + 1]);
         else if (strcmp(argv[p], "-mode") == 0) mode = atoi(argv[p + 1]);
         else if (strcmp(argv[p], "-walk") == 0) walk = atoi(argv[p + 1]);
+        else if (strcmp(argv[p], "-chunk") == 0) chunk = atoi(argv[p + 1]);
         else if (strcmp(argv[p], "-option") == 0) {
             option = atoi(argv[p + 1]);
             if (option == 5) algoname = "Force2Vec:t-distribution with negative sampling";
@@ -95,6 +97,7 @@ int main(int argc, char* argv[]) {
     algo.gpus = gpus;
     algo.epoch_mode = mode;
     algo.walk_sampler = walk;
+    algo.chunk = (uint32_t)(chunk > 0 ? chunk : 0);
     cout << "Running: " << algoname << endl;
     vector<float> outputvec;
     if (option == 5)

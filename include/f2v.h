@@ -122,8 +122,8 @@ int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows,
  * ranges in natural order (algorithms.cpp:569-640), consuming the resident negative
  * stream (ceil(n/batch)*W entries) and, for model 7, the resident walks.  Same result
  * as a loop of f2v_step.  Asynchronous on the engine's stream.
- * chunk: hub rows longer than `chunk` edges are split across warps (0 = default: 256 for dim >= 128,
- * else 128; 64 on a multi-GPU engine whose share of a minibatch is below 16 K rows).  Results are bit-identical
+ * chunk: hub rows longer than `chunk` edges are split across warps (0 = default: 256 for dim >= 128
+ * and batches of >= 16 K rows, else 128; 64 on a multi-GPU engine whose share of a minibatch is below 16 K rows).  Results are bit-identical
  * across world sizes and epoch modes for equal `chunk`.                                */
 int f2v_run_epoch(f2v_engine* e, int model, uint32_t batch, uint32_t s, int bs_mode,
                   float lr, uint32_t chunk);

@@ -15,3 +15,17 @@ fi
 # cfg5 row-sharded (what BASELINE names): each GPU stores 1/8 of both tables
 timeout 1500 $TR --master-port 29713 bench.py --gpus 8 --workload cfg5 --sharded 1 --steps 2 --warmup 1 --no-extra > $O/bench_cfg5_n8_sharded.json 2> $O/bench_cfg5_n8_sharded.err; tail -3 $O/bench_cfg5_n8_sharded.err; cut -c1-1500 $O/bench_cfg5_n8_sharded.json
 ls -la /dev/shm | head; du -sh $O
+# the drop-in CLI on 1 and 8 GPUs of this node (one process, one host thread per GPU, NVLink multicast): whole-run
+# wall as the reference reports it (Results.txt: init + epochs), R-MAT-20 from the binary CSR cache
+python - <<'PY'
+import sys; sys.path.insert(0, '.')
+from force2vec_b200 import host
+rp, ci = host.rmat_csr_cached(20, 16, 1)
+import numpy as np
+host.write_csr('/dev/shm/rmat20.f2vcsr', np.ascontiguousarray(rp), np.ascontiguousarray(ci))
+PY
+mkdir -p /tmp/cli1 /tmp/cli8
+(cd /tmp/cli1 && $OLDPWD/bin/Force2Vec -input /dev/shm/rmat20.f2vcsr -output /tmp/cli1/ -iter 50 -batch 65536 -dim 128 -option 6 -chunk 64 > $OLDPWD/$O/cli_gpus1.log 2>&1; cat Results.txt >> $OLDPWD/$O/cli_results.txt)
+(cd /tmp/cli8 && $OLDPWD/bin/Force2Vec -input /dev/shm/rmat20.f2vcsr -output /tmp/cli8/ -iter 50 -batch 65536 -dim 128 -option 6 -chunk 64 -gpus 8 > $OLDPWD/$O/cli_gpus8.log 2>&1; cat Results.txt >> $OLDPWD/$O/cli_results.txt)
+cmp /tmp/cli1/*.embd /tmp/cli8/*.embd && echo "CLI -gpus 8 .embd == -gpus 1 .embd (byte-identical)" >> $O/cli_results.txt
+cat $O/cli_results.txt; tail -3 $O/cli_gpus8.log
