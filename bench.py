@@ -633,7 +633,21 @@ def bounded_cpu_baseline(a, host):
                        "a full epoch of the headline workload on the CPU is what `--impl reference` times" % (b.scale, a.scale))}
 
 
+def host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank unless it is set; the host side of the
+    library (R-MAT generator, jump-ahead init draws, plan builder) is OpenMP code and the serial phases run on
+    ONE rank while the others wait at a barrier (R-MAT 24 took 140 s instead of 11 s under torchrun).  Rank 0
+    gets every core, the other ranks their share.  Must run before libgomp is loaded (torch, libf2v.so)."""
+    if os.environ.get("F2V_KEEP_OMP_NUM_THREADS") == "1":
+        return
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores if rank == 0 else max(1, cores // max(world, 1)))
+
+
 def main():
+    host_threads()
     a = parse()
     # stdout carries exactly one JSON line: anything libraries print on fd 1 (NCCL's version banner,
     # the reference's progress lines) goes to stderr instead

@@ -1,6 +1,8 @@
 """Worker for tests/test_multi_gpu.py (one rank per GPU under torch.distributed.run)."""
 import os
 import sys
+# torch.distributed.run exports OMP_NUM_THREADS=1: the host side of the library is OpenMP code
+os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 import numpy as np
 import torch
 import torch.distributed as dist

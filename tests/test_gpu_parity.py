@@ -301,36 +301,6 @@ def test_cli_drop_in(oracle, tmp_path):
     assert len(res) == 3 and res[0].startswith("Algo:Force2Vec:t-distribution with negative sampling\tInit:RAND\tIteration:3\t")
 
 
-def test_reference_cli_bound_to_libf2v_equals_drop_in_cli(tmp_path):
-    """The drop-in boundary, proven: oracle/_ref/Force2Vec_f2v is the REFERENCE's own driver, loaders
-    and class (Test/Force2Vec.cpp, IO.h/CSC.h/CSR.h, algorithms.h incl. its writeToFile) compiled with
-    the five hot-path method bodies replaced by INTEGRATION.md section B's binding (oracle/ref_binding.cpp
-    -> f2v_train in libf2v.so).  Its .embd must be byte-identical to bin/Force2Vec's (our loader, our
-    writer, the same engine) for options 5/6/7, bs 0/1 -- and its Results.txt row has the same shape."""
-    ref = os.path.join(ROOT, "oracle", "_ref", "Force2Vec_f2v")
-    exe = os.path.join(ROOT, "bin", "Force2Vec")
-    if not os.path.exists(ref):
-        pytest.skip("oracle/_ref/Force2Vec_f2v not built (needs /root/reference at build time)")
-    cases = [("cora.mtx", 5, 0, 128, 256, 3), ("cora.mtx", 5, 1, 64, 384, 2), ("cora.mtx", 6, 0, 128, 256, 3),
-             ("cora.mtx", 6, 1, 64, 100, 2), ("cora.mtx", 7, 0, 64, 256, 3), ("karate.mtx", 5, 0, 16, 8, 5)]
-    for k, (g, opt, bs, dim, batch, it) in enumerate(cases):
-        outs = []
-        for who, binary in (("ref", ref), ("ours", exe)):
-            d = tmp_path / ("%s%d" % (who, k))
-            d.mkdir()
-            r = subprocess.run([binary, "-input", os.path.join(GOLDEN, g), "-output", str(d) + "/", "-iter", str(it),
-                                "-batch", str(batch), "-dim", str(dim), "-nsamples", "5", "-option", str(opt), "-bs", str(bs)],
-                               capture_output=True, cwd=str(d))
-            assert r.returncode == 0, (who, r.stdout[-500:], r.stderr[-500:])
-            embd = [f for f in os.listdir(d) if f.endswith(".embd")]
-            assert len(embd) == 1, embd
-            outs.append((embd[0], (d / embd[0]).read_bytes(), (d / "Results.txt").read_text()))
-        assert outs[0][0] == outs[1][0]                       # same output file name
-        assert outs[0][1] == outs[1][1], (g, opt, bs)         # same bytes
-        strip = lambda row: row.split("\tTime(sec.):")[0]
-        assert strip(outs[0][2]) == strip(outs[1][2])
-
-
 def test_full_size_rmat20_properties(oracle):
     """BASELINE config 2 at full size (R-MAT scale 20, option 6, d=128): the whole epoch against
     the oracle on the box's host cores, determinism, and the zero-degree closed form."""
