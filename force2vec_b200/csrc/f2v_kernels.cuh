@@ -847,15 +847,6 @@ __device__ __forceinline__ void publish_step(const BatchParams& p, uint64_t step
     for (uint32_t r = 0; r < p.n_peers; r++) st_release_sys(p.peer_flag[r], step);
 }
 
-// The same wait done by one warp on its own (lanes 0..world-1 poll one flag each): used after the
-// warp's griddepcontrol.wait, where a CTA-wide barrier would serialise the warps' prologues.
-__device__ __forceinline__ void peer_wait_warp(const BatchParams& p, int lane) {
-    if (p.wait_step == 0) return;
-    if ((uint32_t)lane < p.world && ((uint32_t)lane != p.rank || p.mc_flag != nullptr))
-        wait_flag(p.flags + (size_t)lane * kFlagStride, p.wait_step, p.timeout_ns, p.timed_out);
-    __syncwarp();
-}
-
 // Predecessor complete (the caller has passed griddepcontrol.wait, or the launch is an ordinary
 // stream-ordered one): its rows are performed in every replica, so its step can be published.
 __device__ __forceinline__ void publish_predecessor(const BatchParams& p) {
