@@ -417,3 +417,32 @@ def test_host_errors_carry_a_message(tmp_path):
     with pytest.raises(F.F2VError) as ei:
         host.load_csr(str(tmp_path / "nope.f2vcsr"))
     assert "f2v_load_csr" in str(ei.value)
+
+
+def test_bench_arms_share_config_and_thread_setup(monkeypatch):
+    """bench.py: both arms build `config` with the same function (the driver compares the dicts), the default
+    workload is the configuration BASELINE quotes "1/2/4/8 B200" on, and the host thread count is taken back from
+    torch.distributed.run's OMP_NUM_THREADS=1 before libgomp is loaded."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.scale, a.model, a.dim, a.bs) == (24, 5, 128, 1)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "4"])
+    b = bench.parse()
+    assert bench.config_of(a, 1 << 24, 520757804) == bench.config_of(b, 1 << 24, 520757804)
+    assert bench.workload_name(a).startswith("rmat24_ef16_seed1 option5(tForce2Vec) d128 s5 bs1 B")
+    cap = bench.committed_capture(a, 1)
+    assert cap and cap["dram_bytes_per_epoch"] < cap["algorithmic_bytes_per_epoch"]      # traffic <= algorithmic bytes
+    assert bench.committed_capture(a, 8) is None                                          # never a constant across N
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.delenv("F2V_KEEP_OMP_NUM_THREADS", raising=False)
+    bench.host_threads()
+    assert int(os.environ["OMP_NUM_THREADS"]) == (os.cpu_count() or 1)
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    bench.host_threads()
+    assert int(os.environ["OMP_NUM_THREADS"]) == max(1, (os.cpu_count() or 1) // 4)
