@@ -446,3 +446,35 @@ def test_bench_arms_share_config_and_thread_setup(monkeypatch):
     monkeypatch.setenv("LOCAL_RANK", "3")
     bench.host_threads()
     assert int(os.environ["OMP_NUM_THREADS"]) == max(1, (os.cpu_count() or 1) // 4)
+
+
+def test_plan_at_scale26_keeps_64bit_edge_offsets():
+    """BASELINE config 5 on the host side: n = 2^26 vertices and more than 2^32 CSR entries -- past the reference's
+    32-bit `INDEXTYPE` (sample/algorithms.h:40, utility.h:128 `my_malloc(unsigned int)`).  The work plan of one of
+    8 ranks (degree-balanced ownership, hub rows cut into chunks) must keep every edge offset as a 64-bit value,
+    cover this rank's rows exactly once and give the 8 ranks equal shares of the edges.  (A synthetic power-law
+    degree sequence stands in for the R-MAT graph: the plan is a function of rowptr only.)"""
+    n, batch, world, chunk = 1 << 26, 262144, 8, 256
+    rng = np.random.default_rng(5)
+    deg = np.minimum((rng.pareto(1.2, n) * 20).astype(np.uint64), 3_000_000)
+    deg[:4096] += rng.integers(100_000, 900_000, 4096).astype(np.uint64)      # hubs at the low ids, like un-permuted R-MAT
+    rp = np.zeros(n + 1, np.uint64)
+    np.cumsum(deg, out=rp[1:])
+    assert int(rp[-1]) > (1 << 32)
+    shares = []
+    for rank in (0, 5):
+        pl = host.plan_build(rp, batch, chunk, rank=rank, world=world, par=9472, assign=1 | 2)
+        it = pl["items"]
+        ln = (it["len"] & 0x7fffffff).astype(np.int64)
+        assert pl["nb"] == n // batch
+        assert int(it["e0"].max()) > (1 << 32)                                  # offsets beyond 32 bits survive
+        plain = (it["len"] & host.CHUNK_FLAG) == 0
+        assert np.array_equal(it["e0"][plain], rp[it["v"][plain]])              # a row's item starts at its rowptr
+        assert np.array_equal(ln[plain], deg[it["v"][plain]].astype(np.int64))
+        rows = np.unique(it["v"])
+        assert len(rows) == plain.sum() + len(np.unique(it["v"][~plain]))       # every owned row: one item or one chunk set
+        shares.append(int(ln.sum()))
+        assert ln[~plain].max() <= chunk
+    total = int(rp[-1])
+    for sh in shares:
+        assert abs(sh - total / world) < 0.02 * total / world                   # LPT partition: equal edge shares
