@@ -478,3 +478,15 @@ def test_plan_at_scale26_keeps_64bit_edge_offsets():
     total = int(rp[-1])
     for sh in shares:
         assert abs(sh - total / world) < 0.02 * total / world                   # LPT partition: equal edge shares
+
+
+def test_create_validates_the_csr_before_touching_a_device():
+    """f2v_create checks rowptr / colids on the host (all threads) and names the first offending entry -- on a
+    box without a GPU too, because the check comes before any CUDA call."""
+    rp = np.array([0, 2, 3, 5], np.uint64)
+    with pytest.raises(F.F2VError) as ei:
+        F.Engine(rp, np.array([1, 2, 0, 7, 9], np.uint32), 8)
+    assert "colids[3] = 7 out of range" in str(ei.value)
+    with pytest.raises(F.F2VError) as ei:
+        F.Engine(np.array([0, 3, 2, 5], np.uint64), np.array([1, 2, 0, 0, 1], np.uint32), 8)
+    assert "rowptr not monotone at row 1" in str(ei.value)
