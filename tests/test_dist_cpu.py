@@ -136,3 +136,28 @@ def test_balanced_partition_two_ranks(model):
             lo, hi = b * batch, min(len(rp) - 1, (b + 1) * batch)
             biggest = int(np.diff(rp64[lo:hi + 1]).max()) + 6
             assert abs(l[0] - l[1]) <= biggest, (b, l, biggest)
+
+
+def test_bench_children_run_in_their_own_process_groups_and_never_cost_the_parent():
+    """bench.py's N = 8 run measures BASELINE config 5 (R-MAT 26) in CHILD processes, one per rank, started by
+    the ranks of the torch.distributed.run job after the headline measurement (bench.cfg5_extras / run_child).
+    Under a real torch.distributed.run (gloo, world 2): a child forms its own process group on a fresh port (the
+    agent store of the parent job must not leak into it), its line comes back, every child's exit code is reported;
+    a crashing child, a child that fails on one rank, a child that hangs past its share of the wall-clock budget
+    (killed) and a run that no longer fits the budget (not started) leave the parent job alive and exiting 0."""
+    import json
+    import subprocess
+    port = 29400 + os.getpid() % 150
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "_child_spawn_worker.py")], capture_output=True, timeout=600)
+    out = r.stdout.decode()
+    assert r.returncode == 0, (out + r.stderr.decode())[-3000:]
+    res = json.loads([ln for ln in out.splitlines() if ln.startswith("PARENT_RESULT ")][-1][len("PARENT_RESULT "):])
+    for key in ("ok", "ok_again"):
+        assert res[key]["pairs_per_s"] == 3.0 and res[key]["n_gpus"] == 2 and res[key]["child_rcs"] == [0, 0]
+        assert res[key]["parity"] == {"bit_exact": True}
+    assert "error" in res["crash"] and res["crash"]["child_rcs"] == [-6, -6]
+    assert res["rank1_fails"]["child_rcs"] == [0, 7]
+    assert res["hang"]["timed_out"] is True and res["hang"]["rc"] == -9
+    assert "skipped" in res["late"]

@@ -45,15 +45,26 @@ def test_reference_cli_bound_to_libf2v_equals_drop_in_cli(tmp_path):
 
 
 
+def _mean_scores_agree(a, b, what):
+    """Two sets of runs (one score per seed each) agree when their means differ by no more than TOL plus three
+    standard errors of that difference (Welch): TOL is the north_star's 0.005, the standard error is what the seed
+    alone moves a score by -- estimated from the runs themselves, so the test does not fail on seed noise and
+    still catches a sampler whose walks are distributed differently (that shifts every seed the same way)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+    diff = abs(a.mean() - b.mean())
+    assert diff <= TOL + 3.0 * se, (what, "libc-walk runs", a.tolist(), "device-sampler runs", b.tolist(), diff, se)
+
+
 def test_option7_device_walk_sampler_scores_match_libc_walks(cora):
     """`-walk 1` (the device sampler: counter-based draws, parallel) cannot consume the serial libc
     stream, so its embeddings are a different random sample, not the reference's bits.  Its parity claim is
-    downstream and statistical: after the full reference configuration (cora, option 7, 1200 epochs) every
-    link-prediction score (accuracy / F1 / AUC) and node-classification F1 lies inside the band that runs
-    walking off the libc-compatible stream (`-walk 0`, the path the reference-golden tests pin) span when only
-    their srand() seed changes (1, 2, 3, 4), widened by the north_star's 0.005 -- same seeded splits everywhere.
-    (Measured once: against a single libc seed every metric was within 0.0053; a +-0.005 comparison between
-    two different random streams tests the seeds as much as the sampler, hence the band.)"""
+    downstream and statistical: after the full reference configuration (cora, option 7, 1200 epochs) the
+    link-prediction scores (accuracy / F1 / AUC) and node-classification F1 of runs that sample on the device
+    have the same mean as runs that walk off the libc-compatible stream (`-walk 0`, the path the
+    reference-golden tests pin), seeds 1..4 each, same seeded evaluation splits everywhere: |difference of the
+    means| <= 0.005 + 3 standard errors.  (Measured once, one run against one run: every metric within 0.0053 --
+    a single pair of runs compares the seeds as much as the samplers, hence the means.)"""
     import evalscores as E
     rp, ci = cora
     labels = E.read_labels(os.path.join(GOLDEN, "cora.nodes.labels"), len(rp) - 1)
@@ -62,16 +73,19 @@ def test_option7_device_walk_sampler_scores_match_libc_walks(cora):
         alg = F.Algorithms(rp, ci, "cora.mtx", "/tmp/", 64)
         alg.walk_sampler, alg.seed = walk, seed
         alg.AlgoForce2VecNSRWEFF(1200, 0, 256, 5, 0.02, write=False)
+        assert np.isfinite(alg.nCoordinates).all()
         lp_ = E.link_prediction(rp, ci, alg.nCoordinates, seeds=(1, 2))
-        nc_ = E.node_classification(alg.nCoordinates, labels, seeds=tuple(range(10)))
-        return lp_, nc_
+        nc_ = E.node_classification(alg.nCoordinates, labels, seeds=tuple(range(5)))
+        return alg.nCoordinates.copy(), lp_, nc_
 
-    libc = [run(0, seed) for seed in (1, 2, 3, 4)]
-    lp, nc = run(1, 1)
+    seeds = (1, 2, 3, 4)
+    libc = [run(0, s) for s in seeds]
+    dev = [run(1, s) for s in seeds]
+    assert not np.array_equal(libc[0][0], dev[0][0])             # different walks, different embeddings
+    assert not np.array_equal(dev[0][0], dev[1][0])              # and the seed reaches the device sampler
     for k in ("accuracy", "f1_macro", "f1_micro", "auc"):
-        lo, hi = min(r[0][k] for r in libc), max(r[0][k] for r in libc)
-        assert lo - TOL <= lp[k] <= hi + TOL, ("link prediction", k, lp[k], lo, hi)
-    for tf in nc:
+        _mean_scores_agree([r[1][k] for r in libc], [r[1][k] for r in dev], ("link prediction", k))
+        assert min(r[1][k] for r in dev) > 0.7                   # and the embedding is a useful one
+    for tf in libc[0][2]:
         for k in ("f1_macro", "f1_micro"):
-            lo, hi = min(r[1][tf][k] for r in libc), max(r[1][tf][k] for r in libc)
-            assert lo - TOL <= nc[tf][k] <= hi + TOL, ("node classification", tf, k, nc[tf][k], lo, hi)
+            _mean_scores_agree([r[2][tf][k] for r in libc], [r[2][tf][k] for r in dev], ("node classification", tf, k))

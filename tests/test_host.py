@@ -61,6 +61,44 @@ def test_loader_matches_reference_semantics(oracle, name):
         assert len(rp) - 1 == 2708 and len(ci) == 10858
 
 
+def _reference_cli_csr(path, workdir):
+    """CSR the REFERENCE's own driver and loaders (Test/Force2Vec.cpp:121-127 with IO.h / CSC.h / CSR.h,
+    compiled from the reference tree: oracle/ref_csr_dump.cpp -> oracle/_ref/Force2Vec_csrdump) hand to the
+    hot-path methods for this file."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "Force2Vec_csrdump")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/Force2Vec_csrdump not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "-input", path, "-output", str(workdir) + "/", "-iter", "1", "-option", "5"],
+                       cwd=str(workdir), capture_output=True)
+    assert r.returncode == 0, (r.stdout[-300:], r.stderr[-300:])
+    raw = open(os.path.join(str(workdir), "csr_dump.bin"), "rb").read()
+    rows, nnz = (int(x) for x in np.frombuffer(raw, np.uint64, 2))
+    return np.frombuffer(raw, np.uint64, rows + 1, 16), np.frombuffer(raw, np.uint32, nnz, 16 + 8 * (rows + 1))
+
+
+def test_loader_equals_the_reference_cli_loader(tmp_path):
+    """f2v_load_mtx builds exactly the CSR the reference's own loader chain builds (same row order, same
+    neighbour order, duplicates / self-loops / mirroring treated alike): the byte-equality of the two CLIs'
+    .embd files (tests/test_gpu_x_boundary_and_sampler.py) rests on it."""
+    rng = np.random.default_rng(7)
+    files = [os.path.join(GOLDEN, "cora.mtx"), os.path.join(GOLDEN, "karate.mtx")]
+    g = tmp_path / "general.mtx"              # duplicates, self-loops, values, comment lines, unsorted entries
+    ent = rng.integers(1, 61, size=(700, 2))
+    g.write_text("%%MatrixMarket matrix coordinate real general\n% made by the test\n60 60 700\n" +
+                 "".join("%d %d %g\n" % (a, b, rng.random()) for a, b in ent))
+    s = tmp_path / "symmetric.mtx"            # lower triangle incl. diagonal entries (dropped by both loaders)
+    low = sorted({(int(max(a, b)), int(min(a, b))) for a, b in rng.integers(1, 81, size=(500, 2))})
+    s.write_text("%%MatrixMarket matrix coordinate pattern symmetric\n80 80 %d\n" % len(low) +
+                 "".join("%d %d\n" % e for e in low))
+    files += [str(g), str(s)]
+    for k, path in enumerate(files):
+        d = tmp_path / ("run%d" % k)
+        d.mkdir()
+        rp_ref, ci_ref = _reference_cli_csr(path, d)
+        rp, ci = host.load_mtx(path)
+        assert np.array_equal(rp, rp_ref) and np.array_equal(ci, ci_ref), path
+
+
 def test_loader_general_and_symmetric(tmp_path, oracle):
     # general: entries kept as they are, including self-loops and duplicates, values ignored
     p = tmp_path / "g.mtx"
