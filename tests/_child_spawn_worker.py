@@ -38,13 +38,13 @@ def parent():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     me = os.path.abspath(__file__)
-    runs = (("ok", ["--child", "ok"], 1), ("crash", ["--child", "crash"], 1), ("rank1_fails", ["--child", "rank1_fails"], 1),
-            ("ok_again", ["--child", "ok"], 1))
+    runs = (("ok", ["--child", "ok"], 1, None), ("not_needed", ["--child", "crash"], 1, "ok"), ("crash", ["--child", "crash"], 1, None),
+            ("after_crash", ["--child", "ok"], 1, "crash"), ("rank1_fails", ["--child", "rank1_fails"], 1, None))
     out = bench.cfg5_extras(dist, rank, world, runs=runs, budget_s=(time.time() - bench.T_START) + 120, script=me)
     # a child that hangs is killed when its share of the budget is over; a run that no longer fits is not started
-    out.update(bench.cfg5_extras(dist, rank, world, runs=(("hang", ["--child", "hang"], 1),),
+    out.update(bench.cfg5_extras(dist, rank, world, runs=(("hang", ["--child", "hang"], 1, None),),
                                  budget_s=(time.time() - bench.T_START) + 34, script=me))
-    out.update(bench.cfg5_extras(dist, rank, world, runs=(("late", ["--child", "ok"], 50),),
+    out.update(bench.cfg5_extras(dist, rank, world, runs=(("late", ["--child", "ok"], 50, None),),
                                  budget_s=(time.time() - bench.T_START) + 10, script=me))
     dist.barrier()
     if rank == 0:

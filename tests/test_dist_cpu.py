@@ -154,7 +154,8 @@ def test_bench_children_run_in_their_own_process_groups_and_never_cost_the_paren
     out = r.stdout.decode()
     assert r.returncode == 0, (out + r.stderr.decode())[-3000:]
     res = json.loads([ln for ln in out.splitlines() if ln.startswith("PARENT_RESULT ")][-1][len("PARENT_RESULT "):])
-    for key in ("ok", "ok_again"):
+    assert "not_needed" not in res                               # a fall-back runs only after the run it stands in for failed
+    for key in ("ok", "after_crash"):
         assert res[key]["pairs_per_s"] == 3.0 and res[key]["n_gpus"] == 2 and res[key]["child_rcs"] == [0, 0]
         assert res[key]["parity"] == {"bit_exact": True}
     assert "error" in res["crash"] and res["crash"]["child_rcs"] == [-6, -6]
