@@ -226,20 +226,112 @@ extern "C" int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint3
     return F2V_OK;
 }
 
+// Semi-random walks off the libc-compatible stream (algorithms.cpp:1097-1118).  The reference's loop is serial by
+// construction -- walk i+1 starts at the stream position where walk i stopped, and how many draws a walk consumes
+// (one per visited vertex of degree > 2) depends on its path -- and every step is two dependent cache misses
+// (rowptr[w], then colids[e]): ~260 ns per start vertex, 1.1 s per epoch at R-MAT 22 against 1.5 ms on the GPU.
+// The numbers cannot change, but the misses can overlap: kWalkers walks are in flight at once, round-robin, each
+// visit doing one half-step and issuing the prefetch for its next one.  A younger walk starts at the stream
+// position its elders are PREDICTED to leave it at (every step still to be decided is assumed to consume a draw);
+// when an elder meets a vertex that consumes nothing the positions of all younger walks move back by one and those
+// that have already used a draw start over (R-MAT 22: 13 % of all steps use no draw, most of them the first step of
+// an isolated start vertex, which is decided before anything younger starts; one walk in five meets a later one,
+// one in three is restarted once).  Walks are committed in order, so the result -- and the stream position
+// afterwards -- is the serial loop's, bit for bit (tests/test_host.py, against the oracle's serial loop).
+namespace {
+struct DrawRing {                    // draws [.., gen) of the stream; a window of kSize behind gen stays readable
+    static constexpr uint64_t kSize = 4096;
+    f2v_rng g;
+    uint64_t gen = 0;
+    uint32_t buf[kSize];
+    explicit DrawRing(const f2v_rng& start) : g(start) {}
+    inline uint32_t at(uint64_t k) {
+        while (gen <= k) { buf[gen & (kSize - 1)] = g.next(); gen++; }
+        return buf[k & (kSize - 1)];
+    }
+};
+struct Walker {
+    uint64_t i, w, e, o;             // start vertex, current vertex, edge index of the current step, first draw
+    uint32_t c, decided, l, phase;   // draws used, steps whose draw decision is made, steps finished, 0 = needs rowptr / 1 = needs colids
+    uint32_t out[F2V_WALKLEN];
+};
+}  // namespace
+
 extern "C" int f2v_draw_walks(f2v_rng* g, uint64_t n, uint64_t nnz, const uint64_t* rowptr,
                               const uint32_t* colids, uint32_t* walks) {
     if (!g || !rowptr || !walks) return f2v::host_fail(F2V_ERR_ARG, "f2v_draw_walks: bad argument or malformed input");
-    for (uint64_t i = 0; i < n; i++) {
-        uint64_t w = i;
-        for (int l = 0; l < F2V_WALKLEN; l++) {
-            const uint64_t dg = rowptr[w + 1] - rowptr[w];
-            uint64_t e = w;   // the reference indexes colids[] with the vertex id here
-            if (dg > 2) e = rowptr[w] + g->next() % (uint32_t)(dg - 1);
-            else if (dg == 2) e = rowptr[w];
-            const uint32_t nx = e < nnz ? colids[e] : (uint32_t)w;
-            walks[i * F2V_WALKLEN + l] = nx;
-            w = nx;
+    constexpr int kWalkers = 24;
+    static_assert((uint64_t)kWalkers * F2V_WALKLEN + 64 < DrawRing::kSize, "draw window too small");
+    const f2v_rng start = *g;
+    DrawRing ring(start);
+    Walker ws[kWalkers];
+    int head = 0, live = 0;                              // ws[(head + k) % kWalkers], k < live: oldest first
+    uint64_t next_i = 0, committed = 0;                  // next start vertex; draws consumed by the committed walks
+    auto slot = [&](int k) -> Walker& { return ws[(head + k) % kWalkers]; };
+    // first half of a step: the draw decision and the edge index; returns whether a draw was used
+    auto decide = [&](Walker& x) -> bool {
+        const uint64_t r0 = rowptr[x.w], dg = rowptr[x.w + 1] - r0;
+        x.e = x.w;                                       // the reference indexes colids[] with the vertex id here
+        x.decided++;
+        const bool draw = dg > 2;
+        if (draw) { x.e = r0 + ring.at(x.o + x.c) % (uint32_t)(dg - 1); x.c++; }
+        else if (dg == 2) x.e = r0;
+        if (x.e < nnz) __builtin_prefetch(colids + x.e, 0, 0);
+        x.phase = 1;
+        return draw;
+    };
+    // (re)start a walk at stream position o.  A start vertex's rowptr entries are sequential reads, so its first
+    // decision (40 % of R-MAT's vertices are isolated) is taken at once, before anything younger is positioned
+    auto start_walk = [&](Walker& x, uint64_t o) {
+        x.w = x.i; x.o = o; x.c = 0; x.decided = 0; x.l = 0; x.phase = 0;
+        decide(x);
+    };
+    // positions of the walks younger than slot k follow from their elders' predictions; a walk whose position
+    // changes after it has used a draw starts over (which changes ITS prediction: keep going down the line)
+    auto reposition = [&](int k) {
+        for (int q = k + 1; q < live; q++) {
+            const Walker& prev = slot(q - 1);
+            Walker& x = slot(q);
+            const uint64_t o = prev.o + prev.c + (F2V_WALKLEN - prev.decided);
+            if (o == x.o) break;                         // nothing further down depends on a changed value
+            if (x.c != 0) start_walk(x, o);
+            else x.o = o;
         }
+    };
+    while (live > 0 || next_i < n) {
+        while (live < kWalkers && next_i < n) {
+            Walker& x = slot(live);
+            x.i = next_i++;
+            start_walk(x, live ? slot(live - 1).o + slot(live - 1).c + (F2V_WALKLEN - slot(live - 1).decided) : committed);
+            live++;
+        }
+        for (int k = 0; k < live; k++) {
+            Walker& x = slot(k);
+            if (x.l == F2V_WALKLEN) continue;            // finished, waits for its elders to commit
+            if (x.phase == 0) {
+                if (!decide(x)) reposition(k);           // no draw used: everything younger moves back by one
+            } else {
+                const uint32_t nx = x.e < nnz ? colids[x.e] : (uint32_t)x.w;
+                x.out[x.l++] = nx;
+                x.w = nx;
+                x.phase = 0;
+                if (x.l < F2V_WALKLEN) __builtin_prefetch(rowptr + nx, 0, 0);
+            }
+        }
+        while (live > 0 && slot(0).l == F2V_WALKLEN) {   // commit in order: the head's position is always exact
+            const Walker& x = slot(0);
+            memcpy(walks + x.i * F2V_WALKLEN, x.out, sizeof(x.out));
+            committed = x.o + x.c;
+            head = (head + 1) % kWalkers;
+            live--;
+        }
+    }
+    // the stream continues after the draws the walks consumed (the ring has drawn a few more)
+    *g = start;
+    if (committed) {
+        uint32_t w[31];
+        rng_window(start, w);
+        *g = rng_jump(w, poly_pow_x(committed));
     }
     return F2V_OK;
 }

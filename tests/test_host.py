@@ -528,3 +528,46 @@ def test_create_validates_the_csr_before_touching_a_device():
     with pytest.raises(F.F2VError) as ei:
         F.Engine(np.array([0, 3, 2, 5], np.uint64), np.array([1, 2, 0, 0, 1], np.uint32), 8)
     assert "rowptr not monotone at row 1" in str(ei.value)
+
+
+def _csr_from_edges(n, edges):
+    adj = [set() for _ in range(n)]
+    for a, b in edges:
+        if a != b:
+            adj[a].add(b)
+            adj[b].add(a)
+    rp = np.zeros(n + 1, np.uint64)
+    ci = []
+    for v in range(n):
+        ci += sorted(adj[v])
+        rp[v + 1] = len(ci)
+    return rp, np.asarray(ci, np.uint32)
+
+
+def test_interleaved_walk_sampler_is_the_serial_loop_bit_for_bit(oracle, cora):
+    """f2v_draw_walks keeps 24 walks in flight (round-robin half-steps with prefetches) and lets a younger walk
+    start at the stream position its elders are predicted to leave; a wrong prediction moves / restarts the younger
+    walks.  Whatever the graph does to the predictions -- every degree <= 2 (all wrong), isolated start vertices
+    whose 'edge index' is their own id, fewer CSR entries than vertices, no edges at all, R-MAT
+    skew -- the walks and the position of the stream afterwards equal the reference's serial loop
+    (algorithms.cpp:1097-1118 as restated in oracle/f2v_oracle.c), over several epochs and seeds."""
+    rng = np.random.default_rng(3)
+    graphs = {
+        "path": _csr_from_edges(50, [(i, i + 1) for i in range(49)]),
+        "star": _csr_from_edges(40, [(0, i) for i in range(1, 40)]),
+        "ring_of_degree_4": _csr_from_edges(30, [(i, (i + 1) % 30) for i in range(30)] + [(i, (i + 2) % 30) for i in range(30)]),
+        "clique_and_56_isolated": _csr_from_edges(64, [(i, j) for i in range(8) for j in range(i + 1, 8)]),
+        "no_edges": (np.zeros(11, np.uint64), np.zeros(0, np.uint32)),
+        "sparse_random": _csr_from_edges(3000, [tuple(int(x) for x in rng.integers(0, 3000, 2)) for _ in range(2500)]),
+        "rmat10": host.rmat_csr(10, 2, 5), "rmat13": host.rmat_csr(13, 16, 5), "rmat15": host.rmat_csr(15, 4, 5),
+        "cora": cora,
+    }
+    for name, (rp, ci) in graphs.items():
+        for seed in (1, 7):
+            g, o = host.RandStream(seed), oracle.Rng(seed)
+            for _ in range(seed % 5):                       # start somewhere inside the stream
+                assert g.rand() == o.rand()
+            for epoch in range(3):
+                got, want = g.walks(rp, ci).copy(), oracle.walks(o, rp, ci)
+                assert np.array_equal(got, want), (name, seed, epoch)
+                assert [g.rand() for _ in range(40)] == [o.rand() for _ in range(40)], (name, seed, epoch)
