@@ -166,3 +166,37 @@ def test_evalscores_reproduce_the_reference_scripts():
         for tf, sc in want["node_classification"].items():
             for k, v in sc.items():
                 assert abs(nc[float(tf)][k] - v) < 1e-9, (seed, tf, k, nc[float(tf)][k], v)
+
+
+def test_evalscores_large_graph_path_follows_the_same_protocol(cora):
+    """The link-prediction harness for graphs where the scripts' Python loop per vertex and a dense feature
+    matrix are infeasible (tools/evalscores.py: link_pairs_vectorised + score_link_split_device -- pairs by array
+    operations, features and the logistic regression on a torch device, the GPU when there is one): the pairs obey
+    the script's rule (every edge u < v once; per vertex twice as many distinct non-neighbours as positives), and on
+    IDENTICAL pairs the device solver gives the scores of the sklearn LogisticRegression the scripts use."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import evalscores as E
+    rp, ci = cora
+    n = len(rp) - 1
+    X = np.load(os.path.join(GOLDEN, "shipped_cora_F2VNS384D128IT1200NS5.npz"))["X"]
+    a, b, y = E.link_pairs_vectorised(rp, ci, 5)
+    a2, b2, y2 = E.link_pairs_vectorised(rp, ci, 5)
+    assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.array_equal(y, y2)          # seeded
+    pos = y == 1
+    adj = [set(ci[int(rp[u]):int(rp[u + 1])].tolist()) for u in range(n)]
+    edges = {(u, v) for u in range(n) for v in adj[u] if v > u}
+    assert set(zip(a[pos].tolist(), b[pos].tolist())) == edges and pos.sum() == len(edges)
+    neg = list(zip(a[~pos].tolist(), b[~pos].tolist()))
+    assert len(set(neg)) == len(neg) and not any(v in adj[u] for u, v in neg)
+    assert np.array_equal(np.bincount(a[~pos], minlength=n), 2 * np.bincount(a[pos], minlength=n))
+    F = np.asarray(X, np.float64)[a] * np.asarray(X, np.float64)[b]
+    want = E.score_link_split(F, y)
+    got = E.score_link_split_device(X, a, b, y, device="cpu")
+    for k in ("accuracy", "f1_macro", "f1_micro", "auc"):
+        assert abs(got[k] - want[k]) < 2e-3, (k, got[k], want[k])
+    # a vertex adjacent to more than half of the graph gets (n - deg) / 2 negatives (runlinkpredict.py:74-75)
+    star_rp = np.concatenate([[0], [9], 9 + np.arange(1, 10)]).astype(np.uint64)
+    star_ci = np.concatenate([np.arange(1, 10), np.zeros(9)]).astype(np.uint32)
+    a, b, y = E.link_pairs_vectorised(star_rp, star_ci, 1)
+    assert (y == 1).sum() == 9 and ((a == 0) & (y == 0)).sum() == (10 - 9) // 2
