@@ -16,11 +16,18 @@ value    = pair updates / s, inputs resident in HBM, CUDA events around K epochs
            on its own device -- bit for bit -- and the line carries "parity"; a mismatch exits non-zero.
 e2e      = the same through f2v_run_epoch_host: pinned HOST table + sample stream in, HOST table out,
            every step (PCIe copies inside the timed region; N > 1: each rank moves its 1/N share of the
-           table over its own PCIe link, the rest travels over NVLink)
+           table over its own PCIe link, the rest travels over NVLink).  The e2e epochs upload the same
+           W + K negative streams the resident epochs used (one per step, from pinned host memory).
 roofline = algorithmic bytes per force-kernel launch / its average duration over the timed region
-           (bytes per epoch = (nnz + n*s)*d*4 read + n*d*4 written); frac_dram = DRAM
+           (bytes per epoch = (nnz + n*s)*d*4 read + n*d*4 written), PER GPU at N > 1 (a
+           rank's launch processes 1/N of the minibatch's pairs; the peak is one GPU's); frac_dram = DRAM
            bytes measured by ncu for this workload and N (profiles/traffic.json) / epoch time / peak
 cpu_baseline = the unmodified reference (oracle/_ref) on this box's host cores, bounded sample
+extra    = N = 1: the other BASELINE configs that fit one GPU (cfg2, cfg2 at batch 256, cfg3, cfg1 through
+           f2v_train).  N = 8: BASELINE configs[4] -- R-MAT scale 26, which the reference cannot address --
+           measured in CHILD processes (one `bench.py --workload cfg5` per rank, own process group, killed
+           with their session at the end of a wall-clock budget: cfg5_extras), replicated and row-sharded,
+           each with the checked epoch; a child's failure is an {"error": ...} entry, never a lost line.
 """
 import argparse
 import json
@@ -63,7 +70,7 @@ def parse():
     ap.add_argument("--bs", type=int)
     ap.add_argument("--lr", type=float, default=0.02)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--mode", type=int, default=0, help="engine epoch mode (0 per-minibatch launches, 1 persistent)")
+    ap.add_argument("--mode", type=int, default=0, help="engine epoch mode (0 per-minibatch launches, 2 one dataflow launch per epoch)")
     ap.add_argument("--variant", type=int, default=-1, help="kernel lane layout (f2v_set_option; -1 = auto)")
     ap.add_argument("--neg-smem", type=int, default=1)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
