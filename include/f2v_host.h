@@ -34,7 +34,9 @@ uint64_t f2v_neg_stream_len(int model, uint64_t n, uint32_t batch, uint32_t s, i
  * 577-578, 686-687, 812-816, 964-967; model 7: range min((b+1)*batch, n-1), :1125-1126). */
 int f2v_draw_epoch_negatives(f2v_rng* g, int model, uint64_t n, uint32_t batch, uint32_t s,
                              int bs_mode, uint32_t* out);
-/* Serial semi-random walks off the same stream (algorithms.cpp:1097-1118): n*5 entries.   */
+/* Semi-random walks off the same stream, the reference's serial loop bit for bit (algorithms.cpp:1097-1118;
+ * n*5 entries, and the stream is left where that loop leaves it).  Internally 24 walks are in flight at
+ * speculative stream positions so that their cache misses overlap; they are committed in order.          */
 int f2v_draw_walks(f2v_rng* g, uint64_t n, uint64_t nnz, const uint64_t* rowptr,
                    const uint32_t* colids, uint32_t* walks);
 
