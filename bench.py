@@ -209,7 +209,7 @@ def _cpu_reference(a, rp, ci, epochs, warm):
     from oracle import oracle as O
     rp, ci = np.ascontiguousarray(rp), np.ascontiguousarray(ci)
     n, nnz = len(rp) - 1, len(ci)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     if not O.ref_available():
         # the reference could not be compiled: time the oracle port instead
         t0 = time.time()
@@ -764,6 +764,15 @@ def bounded_cpu_baseline(a, host):
                        "a full epoch of the headline workload on the CPU is what `--impl reference` times" % (b.scale, a.scale))}
 
 
+def usable_cores():
+    """Cores this process may run on (the affinity mask / cpuset, which a container lease can set below the
+    machine's core count), not the machine's."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def host_threads():
     """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank unless it is set; the host side of the
     library (R-MAT generator, jump-ahead init draws, plan builder) is OpenMP code and the serial phases run on
@@ -773,7 +782,7 @@ def host_threads():
         return
     world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
     rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     os.environ["OMP_NUM_THREADS"] = str(cores if rank == 0 else max(1, cores // max(world, 1)))
 
 

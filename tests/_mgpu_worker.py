@@ -2,7 +2,7 @@
 import os
 import sys
 # torch.distributed.run exports OMP_NUM_THREADS=1: the host side of the library is OpenMP code
-os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 import numpy as np
 import torch
 import torch.distributed as dist

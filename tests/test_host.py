@@ -480,10 +480,10 @@ def test_bench_arms_share_config_and_thread_setup(monkeypatch):
     monkeypatch.setenv("LOCAL_RANK", "0")
     monkeypatch.delenv("F2V_KEEP_OMP_NUM_THREADS", raising=False)
     bench.host_threads()
-    assert int(os.environ["OMP_NUM_THREADS"]) == (os.cpu_count() or 1)
+    assert int(os.environ["OMP_NUM_THREADS"]) == bench.usable_cores() == len(os.sched_getaffinity(0))
     monkeypatch.setenv("LOCAL_RANK", "3")
     bench.host_threads()
-    assert int(os.environ["OMP_NUM_THREADS"]) == max(1, (os.cpu_count() or 1) // 4)
+    assert int(os.environ["OMP_NUM_THREADS"]) == max(1, bench.usable_cores() // 4)
 
 
 def test_plan_at_scale26_keeps_64bit_edge_offsets():
