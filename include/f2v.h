@@ -113,7 +113,8 @@ int f2v_sample_walks(f2v_engine* e, uint64_t seed, uint64_t epoch);
  * X sees the pre-step table, then the rows are replaced (algorithms.cpp:588-639,
  * 833-921, 1142-1193).  neg_idx_host: s entries (bs_mode 0 / model 7) or nrows+s-1
  * (bs_mode 1).  walks_host: n*5 or NULL to use the resident walks.  Teacher-forced
- * entry point used by the parity tests; synchronous.                                  */
+ * entry point used by the parity tests; synchronous.  Hub rows are cut at 128 edges
+ * (= f2v_run_epoch with chunk 128: bit-identical to the epoch's minibatch for that chunk). */
 int f2v_step(f2v_engine* e, int model, uint64_t first_row, uint32_t nrows,
              const uint32_t* neg_idx_host, uint32_t s, int bs_mode, float lr,
              const uint32_t* walks_host);
