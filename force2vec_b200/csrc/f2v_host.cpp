@@ -342,13 +342,17 @@ static int csr_from_pairs(uint64_t n, std::vector<uint32_t>& src, std::vector<ui
     const uint64_t m = src.size();
     uint64_t* rowptr = (uint64_t*)calloc(n + 1, sizeof(uint64_t));
     if (!rowptr) return f2v::host_fail(F2V_ERR_NOMEM, "csr_from_pairs: out of host memory");
-    for (uint64_t k = 0; k < m; k++) rowptr[src[k] + 1]++;
+    // counting and scattering with all host threads: the order in which a row's entries arrive does not matter,
+    // every row is sorted below (equal column ids are indistinguishable)
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)m; k++) __atomic_fetch_add(&rowptr[src[k] + 1], 1ull, __ATOMIC_RELAXED);
     for (uint64_t i = 0; i < n; i++) rowptr[i + 1] += rowptr[i];
     uint32_t* colids = (uint32_t*)malloc(sizeof(uint32_t) * (m ? m : 1));
     if (!colids) { free(rowptr); return f2v::host_fail(F2V_ERR_NOMEM, "csr_from_pairs: out of host memory"); }
     {
         std::vector<uint64_t> cur(rowptr, rowptr + n);
-        for (uint64_t k = 0; k < m; k++) colids[cur[src[k]]++] = dst[k];
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < (int64_t)m; k++) colids[__atomic_fetch_add(&cur[src[k]], 1ull, __ATOMIC_RELAXED)] = dst[k];
     }
     std::vector<uint32_t>().swap(src);
     std::vector<uint32_t>().swap(dst);
