@@ -392,6 +392,9 @@ def run_child(argv, port, timeout_s, script=None):
     env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}
     env["MASTER_PORT"] = str(port)
     env.setdefault("MASTER_ADDR", "127.0.0.1")
+    # the child's NCCL only carries barriers and one-element reductions: keep its communicator off the NVLink
+    # multicast (NVLS) resources, which the parent's communicator and the engine's own multicast object use
+    env.setdefault("NCCL_NVLS_ENABLE", "0")
     t0 = time.time()
     res = {"rc": None, "timed_out": False, "line": None}
     try:
