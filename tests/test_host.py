@@ -308,6 +308,27 @@ def test_shard_row_is_a_dense_bijection_that_spreads_hubs(lg):
     assert cnt.max() <= 2.0 * len(hubs) / world, cnt                              # vs j mod world: almost all on shard 0
 
 
+def test_shard_row_at_scale26_on_eight_gpus_stays_inside_32_bits():
+    """BASELINE config 5 row-sharded: 2^26 vertices over 8 GPUs.  Combined row ids (both tables in one flat range:
+    row of table 1 = rows_alloc + row) must fit 32 bits -- the kernels keep them in uint32 and widen only when they
+    multiply by the row length -- and the placement must still be a bijection.  The C function (the kernels' own
+    __host__ __device__ shard_row) is checked against a vectorised restatement on all 67 M ids."""
+    L = F.lib()
+    lg, n = 3, 1 << 26
+    rows = n >> lg
+    j = np.arange(n, dtype=np.uint64)
+    h = j >> np.uint64(lg)
+    mix = (h * np.uint64(0x9E3779B1)) >> np.uint64(32)
+    r = ((j ^ mix) & np.uint64((1 << lg) - 1)) * np.uint64(rows) + h
+    assert int(r.max()) == n - 1 and 2 * n - 1 < 2**32                            # table 1's last row: n + (n - 1)
+    seen = np.zeros(n, bool)
+    seen[r.astype(np.int64)] = True
+    assert seen.all()                                                             # onto [0, n): a bijection
+    assert np.bincount((r // np.uint64(rows)).astype(np.int64), minlength=8).tolist() == [rows] * 8
+    probe = np.concatenate([np.arange(0, 4096), np.arange(n - 4096, n), np.random.default_rng(1).integers(0, n, 20000)])
+    assert all(L.f2v_shard_row(int(v), lg, rows) == int(r[v]) for v in probe)
+
+
 def test_multi_gpu_driver_without_gpus_fails_loudly():
     """f2v_train_gpus asks for more devices than exist (none here): an error, never a CPU fallback."""
     if F.lib().f2v_device_count() >= 2:
