@@ -246,6 +246,11 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if (1 << a.scale) * a.dim >= 2**32:
+        # sample/algorithms.h:40,68 and algorithms.cpp:593: 32-bit `i*DIM` -- the reference cannot address this table
+        print(json.dumps({"impl": "reference", "unavailable": "the reference indexes the embedding table with 32-bit i*DIM: "
+                          "n*dim = 2^%d is out of its range (sample/algorithms.h:40,68)" % (a.scale + (a.dim - 1).bit_length())}), flush=True)
+        return
     rp, ci, _ = make_graph(a)
     n, nnz = len(rp) - 1, len(ci)
     epochs = 1 if (a.scale >= 22 or a.steps < 2) else min(a.steps, 3)
