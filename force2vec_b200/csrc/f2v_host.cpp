@@ -895,8 +895,14 @@ extern "C" int f2v_train_gpus(const f2v_train_args* a, int gpus, float* X_out, d
         };
         step(f2v_create(&e, a->device + r, a->n, a->nnz, a->rowptr, a->colids, a->dim));
         if (!rc && a->epoch_mode) step(f2v_set_epoch_mode(e, a->epoch_mode));
-        // one host thread per engine: the engines of this process may use the NVLink multicast exchange
-        if (!rc) step(f2v_set_option(e, "multicast_in_process", 1));
+        // one host thread per engine, so the engines of this process COULD run the (blocking) NVLink multicast
+        // hand-off among themselves -- but that set-up has only ever run between processes (two in-process engines
+        // exchange with one store per peer by the N = 2 rule), so it is opt-in here (F2V_INPROC_MULTICAST=1) and the
+        // default for engines of one process is plain peer access with one store per peer
+        if (!rc) {
+            const char* mc = getenv("F2V_INPROC_MULTICAST");
+            if (mc && atoi(mc) != 0) step(f2v_set_option(e, "multicast_in_process", 1));
+        }
         if (!rc) step(f2v_comm_peer_export(e, blobs.data() + (size_t)r * F2V_PEER_BLOB));
         bool stop = bar.wait();
         if (!stop) step(f2v_comm_peer_init(e, blobs.data(), r, G));

@@ -163,7 +163,8 @@ int f2v_set_epoch_mode(f2v_engine* e, int mode);
  *   "auto_flow" epoch mode 0 switches to the dataflow epoch for batches up to this size (default 0 = never)
  *   "multicast" peer exchange through NVLink multicast stores: 1 (default) when supported, 0 never
  *   "multicast_in_process"  1 = the engines of this process are each driven by their own host thread, so
- *               they may set up the multicast exchange among themselves (f2v_train_gpus sets it)
+ *               they may set up the multicast exchange among themselves (f2v_train_gpus sets it when
+ *               F2V_INPROC_MULTICAST=1; default off: that set-up has only run between processes so far)
  *   "sharded"   1 = row-sharded tables (set on every rank before f2v_comm_peer_export)
  *   "peer_sig"  who publishes a minibatch's exchange step: 2 (default) = CTA 0 of the next launch after
  *               its dependency wait; 1 = a 1-CTA kernel after the force kernel; 0 = the last CTA
