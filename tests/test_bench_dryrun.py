@@ -258,3 +258,21 @@ def test_eight_gpu_children_are_skipped_when_the_budget_is_spent(monkeypatch, ca
     line, _, started, _ = _run(monkeypatch, capsys, ["--gpus", "8", "--no-e2e"], world=8, children=lambda argv: None)
     assert started == [] and all("skipped" in v for v in line["extra"].values()) and len(line["extra"]) == 2   # (no fall-back either)
     assert line["e2e"] is None and line["value"] > 0
+
+
+def test_eight_gpu_watchdog_prints_the_headline_if_the_extras_never_return(monkeypatch, capsys):
+    """Should the machinery around the scale-26 children hang, every rank leaves on its own shortly after the
+    budget and rank 0 has printed the headline line by then -- once."""
+    import time
+    monkeypatch.setenv("F2V_BENCH_BUDGET_S", "-1000")                # the deadline has passed before the extras start
+    monkeypatch.setattr(np, "save", lambda *a, **k: None)
+    monkeypatch.setattr(os, "replace", lambda *a, **k: None)
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(bench, "shared_init", lambda a, n, host, dist, rank: (
+        host.RandStream(1).init_embeddings(a.model, n, a.dim), host.RandStream(1)))
+    exits = []
+    monkeypatch.setattr(bench, "_exit", lambda code: exits.append(code))
+    monkeypatch.setattr(bench, "cfg5_extras", lambda *a, **k: (time.sleep(2.5), {"late": 1})[1])     # "hangs" past the deadline
+    line, _, _, _ = _run(monkeypatch, capsys, ["--gpus", "8", "--no-e2e"], world=8)
+    assert exits and set(exits) == {0}
+    assert "watchdog" in line["extra"]["error"] and line["value"] > 0 and line["n_gpus"] == 8
