@@ -27,8 +27,6 @@ def main():
     ap.add_argument("--modes", default="0")
     ap.add_argument("--negsmem", default="1")
     ap.add_argument("--pars", default="9472")
-    ap.add_argument("--prefetch", default="0")
-    ap.add_argument("--persist", default="0")
     ap.add_argument("--pdl", default="2")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="")
@@ -49,22 +47,13 @@ def main():
     for B, var, ch, mode, ns, par in itertools.product([int(x) for x in a.batches.split(",")], [int(x) for x in a.variants.split(",")],
                                                        [int(x) for x in a.chunks.split(",")], [int(x) for x in a.modes.split(",")],
                                                        [int(x) for x in a.negsmem.split(",")], [int(x) for x in a.pars.split(",")]):
-      for pf, ps, pdl in itertools.product([int(x) for x in a.prefetch.split(",")], [int(x) for x in a.persist.split(",")],
-                                           [int(x) for x in a.pdl.split(",")]):
+      for pdl in [int(x) for x in a.pdl.split(",")]:
             neg = g.epoch_negatives(a.model, n, B, 5, a.bs).copy()
             eng.set_negatives(neg)
             eng.set_option("variant", var)
             eng.set_option("neg_smem", ns)
-            try:
-                eng.set_option("prefetch", pf)
-                eng.set_option("persist", ps)
-                eng.set_option("pdl", pdl)
-            except F.F2VError:
-                pass
-            try:
-                eng.set_option("par", par)
-            except F.F2VError:
-                pass
+            eng.set_option("pdl", pdl)
+            eng.set_option("par", par)
             try:
                 eng.set_epoch_mode(mode)
             except F.F2VError as ex:
@@ -77,7 +66,7 @@ def main():
                 eng.run_epoch(a.model, B, 5, a.bs, 0.02, ch)
                 ms.append(eng.last_epoch_ms())
             best = min(ms)
-            row = {"B": B, "variant": var, "chunk": ch, "mode": mode, "neg_smem": ns, "par": par, "prefetch": pf, "persist": ps, "pdl": pdl, "ms": best, "ms_all": ms,
+            row = {"B": B, "variant": var, "chunk": ch, "mode": mode, "neg_smem": ns, "par": par, "pdl": pdl, "ms": best, "ms_all": ms,
                    "Gpairs_s": pairs / best / 1e6, "GBs": byts / best / 1e6, "frac": byts / best / 1e6 / 6553.3}
             rows.append(row)
             print(json.dumps(row), flush=True)
