@@ -4,7 +4,7 @@
 // class (sample/algorithms.h: constructor, nCoordinates, writeToFile): the five hot-path method bodies
 // (sample/algorithms.cpp:544-652, 654-753, 778-932, 934-1060, 1063-1203) become calls into libf2v.so
 // through the C ABI (include/f2v.h, include/f2v_host.h).  Test infrastructure: oracle/Makefile builds
-// oracle/_ref/Force2Vec_f2v from it where /root/reference exists; tests/test_gpu_parity.py checks that
+// oracle/_ref/Force2Vec_f2v from it where /root/reference exists; tests/test_gpu_x_boundary_and_sampler.py checks that
 // its .embd is byte-identical to bin/Force2Vec's.  Nothing of the reference is copied: its headers and
 // driver are compiled from where they lie.
 #include "f2v.h"
