@@ -221,3 +221,22 @@ def test_oracle_vs_live_reference_on_a_skewed_graph(oracle, opt, bs, dim, B, it)
     np.testing.assert_allclose(Xo, Xr, rtol=0, atol=2e-6)
     if opt == 6:
         assert np.array_equal(Xo, Xr)
+
+
+def test_oracle_vs_live_reference_on_the_edge_cases_the_gpu_tests_use(oracle):
+    """tests/test_gpu_parity.py::test_edge_cases compares the CUDA path with the oracle for s = 0, s > 32, a batch
+    larger than the graph, a graph without edges and uncommon dimensions; here the oracle itself is compared with the
+    unmodified reference on those shapes (two epochs from srand(1), R-MAT scale 8 and an empty 70-vertex graph)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libf2vref.so not built (needs /root/reference at build time)")
+    from force2vec_b200 import host
+    rp, ci = host.rmat_csr(8, 4, 2)
+    n = len(rp) - 1
+    rp0, ci0 = np.zeros(71, np.uint64), np.zeros(0, np.uint32)
+    cases = [(rp, ci, 5, 0, 32, 37, 40), (rp, ci, 6, 0, 32, 37, 0), (rp, ci, 5, 1, 32, n + 50, 5), (rp, ci, 7, 0, 64, n + 50, 5),
+             (rp0, ci0, 5, 0, 64, 70, 3), (rp0, ci0, 6, 0, 64, 16, 3), (rp, ci, 6, 1, 300, 100, 5), (rp, ci, 5, 0, 256, 64, 33)]
+    for a, b, opt, bs, dim, B, s in cases:
+        Xr, _ = oracle.ref_run(opt, bs, a, b, dim, 2, B, s, 0.02, threads=2)
+        Xo = oracle.run(opt, bs, a, b, dim, 2, B, s, 0.02, threads=2)["X"]
+        assert np.isfinite(Xr).all()
+        np.testing.assert_allclose(Xo, Xr, rtol=0, atol=1e-6, err_msg=str((opt, bs, dim, B, s)))
