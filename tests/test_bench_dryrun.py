@@ -276,3 +276,27 @@ def test_eight_gpu_watchdog_prints_the_headline_if_the_extras_never_return(monke
     line, _, _, _ = _run(monkeypatch, capsys, ["--gpus", "8", "--no-e2e"], world=8)
     assert exits and set(exits) == {0}
     assert "watchdog" in line["extra"]["error"] and line["value"] > 0 and line["n_gpus"] == 8
+
+
+@pytest.mark.parametrize("argv", [["--workload", "cfg5", "--steps", "3", "--warmup", "3", "--no-e2e"],
+                                  ["--workload", "cfg5", "--steps", "3", "--warmup", "3", "--no-e2e", "--multicast", "0"],
+                                  ["--workload", "cfg5", "--sharded", "1", "--steps", "2", "--warmup", "3"]])
+def test_the_scale26_child_command_lines_run_through(monkeypatch, capsys, argv):
+    """The three command lines cfg5_extras gives its children (bench.CFG5_RUNS + the arguments it appends), dry:
+    they parse, take the N = 8 path with the checked epoch, start no children of their own, skip the host-buffer
+    epoch where asked (a row-sharded engine always does) and print one line with the parity field."""
+    bench = importlib.import_module("bench")
+    assert list(argv) in [list(r[1]) for r in bench.CFG5_RUNS]
+    monkeypatch.setattr(np, "save", lambda *a, **k: None)
+    monkeypatch.setattr(os, "replace", lambda *a, **k: None)
+    monkeypatch.setattr(bench, "shared_init", lambda a, n, host, dist, rank: (
+        host.RandStream(1).init_embeddings(a.model, n, a.dim), host.RandStream(1)))
+    called = []
+    monkeypatch.setattr(bench, "cfg5_extras", lambda *a, **k: called.append(1) or {})
+    line, log, _, _ = _run(monkeypatch, capsys, argv + ["--gpus", "8", "--no-extra", "--no-cpu-baseline"], world=8)
+    assert not called and line["extra"] == {} and line["e2e"] is None
+    assert line["parity"]["bit_exact"] is True and line["n_gpus"] == 8 and line["steps"] == int(argv[argv.index("--steps") + 1])
+    assert ("sharded" in line["setup"]["parallelism"]) == ("--sharded" in argv)
+    opts = {x[1]: x[2] for x in log if x[0] == "set_option"}
+    assert opts["sharded"] == (1 if "--sharded" in argv else 0) and opts["multicast"] == (0 if "--multicast" in argv else 1)
+    assert not any(x[0] == "run_epoch_host" for x in log)
